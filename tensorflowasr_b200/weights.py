@@ -1,0 +1,522 @@
+"""Weight import for the B200 Conformer-CTC path.
+
+The reference deploys three tf2onnx files per model (`encoder.onnx`, `ctc_model.onnx`, `translator.onnx`) and
+loads them with onnxruntime (Inference/PythonInference/asr/src/asr.py:22-25).  `import_encoder` /
+`import_ctc_model` read the *same files* and return the parameters in the reference's own (Keras) layout
+-- the "raw" dict -- plus the model geometry.  `pack_for_device` then lays them out for the CUDA kernels
+(K-major `[N, K]` GEMM operands, BatchNorm folded into the preceding pointwise conv, 1/sqrt(head) folded into
+Wq, GLU halves interleaved) as one flat 128-byte aligned float32 blob + name table, consumed by
+`b200asr_create` (include/b200asr.h).
+
+Raw layout (all float32, names follow asr/models/conformer_blocks.py):
+  fe.window [1024]            periodic Hann as baked in the STFT kernels (asr/models/layers/backend.py:57-62)
+  fe.mel    [513, n_mels]     freq2mel (time_frequency.py:157-160)
+  sub.conv1.w [3,3,1,D] (HWIO) sub.conv1.b [D];  sub.conv2.w [3,3,D,D] sub.conv2.b [D]   (conformer_blocks.py:76-85)
+  sub.lin.w [F2*D, D]  sub.lin.b [D]                                                     (:86)
+  per block prefix P = "enc.{i}." / "ctc.blk{i}.":
+    P+ffn{1,2}.ln.g/b [D], .w1 [D,4D], .b1 [4D], .w2 [4D,D], .b2 [D]                      (:107-134)
+    P+mhsa.ln.g/b, .wq/.wk/.wv [H,D,dh], .wo [H,dh,D], .bo [D]                            (multihead_attention.py:76-110)
+    P+conv.ln.g/b, .pw1.w [D,2D], .pw1.b [2D], .dw.w [K,D], .pw.w [D,2D], .pw.b [2D],
+      .bn.scale [2D], .bn.shift [2D] (eval-mode BN folded by tf2onnx, eps 1e-3), .pw2.w [2D,D], .pw2.b [D]   (:182-219)
+    P+ln.g/b [D]                                                                          (:256,264)
+  ctc.proj.w [D,D] ctc.proj.b [D]; ctc.fc.w [D,V] ctc.fc.b [V]                            (:399,413-414)
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, asdict
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .onnx_reader import Graph, Node, load_graph
+
+# --------------------------------------------------------------------------------------------------------
+# constant folding over the tiny op subset tf2onnx leaves around weight operands
+# --------------------------------------------------------------------------------------------------------
+_SHAPE_OPS = {"Reshape", "Transpose", "Squeeze", "Unsqueeze", "Cast", "Identity", "Expand"}
+
+
+class _NotConstant(Exception):
+    pass
+
+
+def _axes_of(node: Node, consts: "ConstEval", default=None):
+    if "axes" in node.attrs:
+        return [int(a) for a in node.attrs["axes"]]
+    if len(node.inputs) > 1 and node.inputs[1]:
+        return [int(a) for a in np.asarray(consts(node.inputs[1])).ravel()]
+    return default
+
+
+class ConstEval:
+    """Evaluate tensors that depend on initializers only."""
+
+    def __init__(self, graph: Graph):
+        self.g = graph
+        self.prod = graph.producer()
+        self.cache: Dict[str, np.ndarray] = {}
+
+    def __call__(self, name: str) -> np.ndarray:
+        if name in self.g.initializers:
+            return self.g.initializers[name]
+        if name in self.cache:
+            return self.cache[name]
+        if name not in self.prod:
+            raise _NotConstant(name)
+        n = self.prod[name]
+        val = self._eval(n)
+        self.cache[name] = val
+        return val
+
+    def is_const(self, name: str) -> bool:
+        try:
+            self(name)
+            return True
+        except _NotConstant:
+            return False
+
+    def _eval(self, n: Node) -> np.ndarray:
+        op = n.op_type
+        if op == "Reshape":
+            x = self(n.inputs[0])
+            shp = [int(s) for s in self(n.inputs[1]).ravel()]
+            shp = [x.shape[i] if s == 0 else s for i, s in enumerate(shp)]
+            return x.reshape(shp)
+        if op == "Transpose":
+            x = self(n.inputs[0])
+            return np.transpose(x, n.attrs.get("perm"))
+        if op == "Squeeze":
+            x = self(n.inputs[0])
+            axes = _axes_of(n, self)
+            return np.squeeze(x, axis=tuple(axes) if axes is not None else None)
+        if op == "Unsqueeze":
+            x = self(n.inputs[0])
+            for a in sorted(_axes_of(n, self)):
+                x = np.expand_dims(x, a)
+            return x
+        if op == "Cast":
+            to = {1: np.float32, 6: np.int32, 7: np.int64, 9: np.bool_, 11: np.float64}[n.attrs["to"]]
+            return self(n.inputs[0]).astype(to)
+        if op == "Identity":
+            return self(n.inputs[0])
+        if op == "Shape":
+            return np.asarray(self(n.inputs[0]).shape, dtype=np.int64)
+        if op == "Gather":
+            x = self(n.inputs[0])
+            idx = self(n.inputs[1])
+            return np.take(x, idx, axis=int(n.attrs.get("axis", 0)))
+        if op == "Concat":
+            return np.concatenate([np.atleast_1d(self(i)) for i in n.inputs], axis=int(n.attrs.get("axis", 0)))
+        if op == "ReduceProd":
+            x = self(n.inputs[0])
+            axes = n.attrs.get("axes")
+            return np.prod(x, axis=tuple(axes) if axes else None, keepdims=bool(n.attrs.get("keepdims", 1)))
+        if op == "Slice":
+            x = self(n.inputs[0])
+            starts = self(n.inputs[1]).ravel()
+            ends = self(n.inputs[2]).ravel()
+            axes = self(n.inputs[3]).ravel() if len(n.inputs) > 3 and n.inputs[3] else np.arange(len(starts))
+            steps = self(n.inputs[4]).ravel() if len(n.inputs) > 4 and n.inputs[4] else np.ones(len(starts), np.int64)
+            sl = [slice(None)] * x.ndim
+            for s, e, a, st in zip(starts, ends, axes, steps):
+                sl[int(a)] = slice(int(s), int(e), int(st))
+            return x[tuple(sl)]
+        if op in ("Mul", "Add", "Sub", "Div"):
+            a, b = self(n.inputs[0]), self(n.inputs[1])
+            return {"Mul": np.multiply, "Add": np.add, "Sub": np.subtract, "Div": np.divide}[op](a, b)
+        raise _NotConstant(f"{n.name} ({op})")
+
+
+# --------------------------------------------------------------------------------------------------------
+# graph walking helpers
+# --------------------------------------------------------------------------------------------------------
+_MATMUL_OPS = {"Gemm", "MatMul", "Einsum", "Conv"}
+
+
+def _effective_weight(n: Node, ce: ConstEval) -> np.ndarray:
+    """The [N, K] matrix W such that node computes A[.., K] @ W.T (A's contracted dims flattened in A's order)."""
+    if n.op_type == "Gemm":
+        b = np.asarray(ce(n.inputs[1]), dtype=np.float32)
+        b = b.reshape(b.shape[-2], b.shape[-1]) if b.ndim > 2 else b
+        return b if int(n.attrs.get("transB", 0)) else b.T
+    if n.op_type == "MatMul":
+        b = np.asarray(ce(n.inputs[1]), dtype=np.float32)
+        b = b.reshape(b.shape[-2], b.shape[-1])
+        return b.T
+    if n.op_type == "Einsum":
+        eq = n.attrs["equation"].decode().replace(" ", "")
+        lhs, out = eq.split("->")
+        a_idx, b_idx = lhs.split(",")
+        b = np.asarray(ce(n.inputs[1]), dtype=np.float32)
+        contracted = [c for c in a_idx if c in b_idx and c not in out]
+        kept = [c for c in out if c in b_idx and c not in a_idx]
+        perm = [b_idx.index(c) for c in kept + contracted]
+        bt = np.transpose(b, perm)
+        nk = int(np.prod([b.shape[b_idx.index(c)] for c in kept]))
+        return bt.reshape(nk, -1)
+    raise ValueError(f"not a matmul-like node: {n.op_type}")
+
+
+class _Walker:
+    def __init__(self, g: Graph):
+        self.g = g
+        self.ce = ConstEval(g)
+        self.prod = g.producer()
+        self.cons = g.consumers()
+        self.by_name = {n.name: n for n in g.nodes}
+
+    def _has_const_operand(self, n: Node) -> bool:
+        return n.op_type in ("Gemm", "MatMul", "Einsum") and len(n.inputs) > 1 and self.ce.is_const(n.inputs[1])
+
+    def back_to_projection(self, tensor: str, limit: int = 64) -> Node:
+        """Follow the data operand backwards through layout-only ops (and scalar scaling) to the first
+        matmul-like node whose second operand is a constant."""
+        t = tensor
+        for _ in range(limit):
+            if t not in self.prod:
+                break
+            n = self.prod[t]
+            if self._has_const_operand(n):
+                return n
+            if n.op_type in _SHAPE_OPS:
+                t = n.inputs[0]
+                continue
+            if n.op_type in ("Mul", "Div"):
+                a, b = n.inputs[0], n.inputs[1]
+                if self.ce.is_const(b) and np.asarray(self.ce(b)).size == 1:
+                    t = a
+                    continue
+                if self.ce.is_const(a) and np.asarray(self.ce(a)).size == 1:
+                    t = b
+                    continue
+            break
+        raise ValueError(f"no constant-weight projection found upstream of {tensor!r}")
+
+    def back_to_dynamic_matmul(self, tensor: str, limit: int = 64) -> Node:
+        t = tensor
+        for _ in range(limit):
+            n = self.prod[t]
+            if n.op_type in ("MatMul", "Einsum") and not self._has_const_operand(n):
+                return n
+            if n.op_type in _SHAPE_OPS:
+                t = n.inputs[0]
+                continue
+            break
+        raise ValueError(f"no activation x activation matmul upstream of {tensor!r}")
+
+    def forward_to_dynamic_matmul(self, tensor: str, limit: int = 64) -> Tuple[Node, int]:
+        t = tensor
+        for _ in range(limit):
+            users = self.cons.get(t, [])
+            nxt = None
+            for u in users:
+                if u.op_type in ("MatMul", "Einsum") and not self._has_const_operand(u):
+                    return u, u.inputs.index(t)
+                if u.op_type in _SHAPE_OPS and u.inputs[0] == t:
+                    nxt = u.outputs[0]
+            if nxt is None:
+                break
+            t = nxt
+        raise ValueError(f"no activation x activation matmul downstream of {tensor!r}")
+
+
+@dataclass
+class ModelGeometry:
+    dmodel: int
+    num_blocks: int
+    num_heads: int
+    head_size: int
+    kernel_size: int
+    ff_dim: int
+    n_mels: int = 80
+    n_dft: int = 1024
+    hop: int = 160
+    vocab: int = 0           # only for ctc models
+    ln_eps: float = 1e-3
+
+    def as_dict(self):
+        return asdict(self)
+
+
+def _find(g: Graph, pattern: str) -> List[str]:
+    rx = re.compile(pattern)
+    return [k for k in g.initializers if rx.search(k)]
+
+
+def _one(g: Graph, pattern: str) -> np.ndarray:
+    hits = _find(g, pattern)
+    if len(hits) != 1:
+        raise KeyError(f"expected exactly one initializer matching {pattern!r}, found {hits}")
+    return np.asarray(g.initializers[hits[0]], dtype=np.float32)
+
+
+def _const_other_input(w: _Walker, node: Node) -> np.ndarray:
+    for i in node.inputs:
+        if w.ce.is_const(i):
+            return np.asarray(w.ce(i), dtype=np.float32)
+    raise KeyError(f"{node.name}: no constant operand")
+
+
+def _import_block(w: _Walker, prefix: str, out_prefix: str, raw: Dict[str, np.ndarray]) -> Tuple[int, int, int]:
+    """Pull one ConformerBlock (conformer_blocks.py:235-265).  `prefix` e.g. 'conformer_block_3/'."""
+    g = w.g
+    P = re.escape(prefix)
+
+    def ln(sub: str, dst: str):
+        raw[dst + ".g"] = _one(g, f"^{P}{sub}layer_normalization(_\\d+)?/mul_3/ReadVariableOp:0$")
+        raw[dst + ".b"] = _one(g, f"^{P}{sub}layer_normalization(_\\d+)?/add/ReadVariableOp:0$")
+
+    for k in (1, 2):
+        sub = f"ff_module_{k}/"
+        dst = f"{out_prefix}ffn{k}"
+        ln(sub, dst + ".ln")
+        kernels = sorted(_find(g, f"^{P}{sub}dense_\\d+/Tensordot/ReadVariableOp:0$"),
+                         key=lambda s: int(re.search(r"dense_(\d+)", s).group(1)))
+        biases = sorted(_find(g, f"^{P}{sub}dense_\\d+/BiasAdd/ReadVariableOp:0$"),
+                        key=lambda s: int(re.search(r"dense_(\d+)", s).group(1)))
+        if len(kernels) != 2 or len(biases) != 2:
+            raise KeyError(f"{prefix}{sub}: expected 2 dense layers, got {kernels}")
+        raw[dst + ".w1"] = np.asarray(g.initializers[kernels[0]], np.float32)
+        raw[dst + ".b1"] = np.asarray(g.initializers[biases[0]], np.float32)
+        raw[dst + ".w2"] = np.asarray(g.initializers[kernels[1]], np.float32)
+        raw[dst + ".b2"] = np.asarray(g.initializers[biases[1]], np.float32)
+
+    # ---- MHSA (multihead_attention.py:151-188): locate Q/K/V/O by walking from the Softmax
+    ln("mhsa_module/", f"{out_prefix}mhsa.ln")
+    softmax = [n for n in g.nodes if n.op_type == "Softmax" and n.name.startswith(prefix + "mhsa_module/")]
+    if len(softmax) != 1:
+        raise KeyError(f"{prefix}: expected one Softmax, got {[n.name for n in softmax]}")
+    sm = softmax[0]
+    scores = w.back_to_dynamic_matmul(sm.inputs[0])
+    q_node = w.back_to_projection(scores.inputs[0])
+    k_node = w.back_to_projection(scores.inputs[1])
+    av, pos = w.forward_to_dynamic_matmul(sm.outputs[0])
+    v_node = w.back_to_projection(av.inputs[1 - pos])
+    bias_add = [n for n in g.nodes if n.op_type == "Add" and
+                re.match(f"^{P}mhsa_module/multi_head_attention(_\\d+)?/add$", n.name)]
+    if len(bias_add) != 1:
+        raise KeyError(f"{prefix}: MHA output bias add not found")
+    bo = _one(g, f"^{P}mhsa_module/multi_head_attention(_\\d+)?/add/ReadVariableOp:0$")
+    data_in = [i for i in bias_add[0].inputs if not w.ce.is_const(i)][0]
+    o_node = w.back_to_projection(data_in)
+    wq, wk, wv = (_effective_weight(n, w.ce) for n in (q_node, k_node, v_node))     # [H*dh, D]
+    wo = _effective_weight(o_node, w.ce)                                             # [D, H*dh]
+    D = wq.shape[1]
+    # head geometry: the out-projection constant keeps its (H, dh) axes somewhere in the graph
+    H = dh = None
+    for node in (o_node, q_node, k_node, v_node):
+        src = node.inputs[1]
+        t = src
+        for _ in range(8):
+            arr = w.g.initializers.get(t)
+            if arr is not None:
+                dims = [d for d in arr.shape if d != 1]
+                if len(dims) == 3:
+                    others = [d for d in dims if d != D] if dims.count(D) == 1 else None
+                    if others and len(others) == 2:
+                        if dims[0] == D:      # (D, H, dh)
+                            H, dh = dims[1], dims[2]
+                        else:                 # (H, dh, D)
+                            H, dh = dims[0], dims[1]
+                break
+            if t in w.prod:
+                t = w.prod[t].inputs[0]
+            else:
+                break
+        if H is not None:
+            break
+    if H is None:
+        raise KeyError(f"{prefix}: cannot infer attention head geometry")
+    mp = f"{out_prefix}mhsa"
+    # back to the Keras layout [H, D, dh] / [H, dh, D]
+    raw[mp + ".wq"] = np.ascontiguousarray(wq.reshape(H, dh, D).transpose(0, 2, 1))
+    raw[mp + ".wk"] = np.ascontiguousarray(wk.reshape(H, dh, D).transpose(0, 2, 1))
+    raw[mp + ".wv"] = np.ascontiguousarray(wv.reshape(H, dh, D).transpose(0, 2, 1))
+    raw[mp + ".wo"] = np.ascontiguousarray(wo.T.reshape(H, dh, D))
+    raw[mp + ".bo"] = bo
+
+    # ---- conv module (conformer_blocks.py:182-219)
+    cp = f"{out_prefix}conv"
+    ln("conv_module/", cp + ".ln")
+    pw1 = _one(g, f"^{P}conv_module/pw_conv_1/conv1d/ExpandDims_1:0$")          # [2D, D, 1, 1] OIHW
+    raw[cp + ".pw1.w"] = np.ascontiguousarray(pw1[:, :, 0, 0].T)
+    raw[cp + ".pw1.b"] = _const_other_input(w, w.by_name[prefix + "conv_module/pw_conv_1/BiasAdd"]).reshape(-1)
+    dw_node = w.by_name[prefix + "conv_module/dw_conv/separable_conv2d/depthwise"]
+    dw = np.asarray(w.ce(dw_node.inputs[1]), np.float32)                         # [D, 1, 1, K]
+    raw[cp + ".dw.w"] = np.ascontiguousarray(dw[:, 0, 0, :].T)                   # [K, D]
+    pw = _one(g, f"^{P}conv_module/dw_conv/ExpandDims_2:0$")                     # [2D, D, 1, 1]
+    raw[cp + ".pw.w"] = np.ascontiguousarray(pw[:, :, 0, 0].T)
+    raw[cp + ".pw.b"] = _one(g, f"^{P}conv_module/dw_conv/BiasAdd/ReadVariableOp:0$")
+    raw[cp + ".bn.scale"] = _one(g, f"^{P}conv_module/batch_normalization(_\\d+)?/batchnorm/mul:0$").reshape(-1)
+    bn_add = [n for n in g.nodes if re.match(f"^{P}conv_module/batch_normalization(_\\d+)?/batchnorm/add_1$", n.name)][0]
+    raw[cp + ".bn.shift"] = _const_other_input(w, bn_add).reshape(-1)
+    pw2 = _one(g, f"^{P}conv_module/pw_conv_2/conv1d/ExpandDims_1:0$")          # [D, 2D, 1, 1]
+    raw[cp + ".pw2.w"] = np.ascontiguousarray(pw2[:, :, 0, 0].T)
+    raw[cp + ".pw2.b"] = _const_other_input(w, w.by_name[prefix + "conv_module/pw_conv_2/BiasAdd"]).reshape(-1)
+
+    # ---- final LN: the one directly under the block prefix
+    raw[f"{out_prefix}ln.g"] = _one(g, f"^{P}layer_normalization(_\\d+)?/mul_3/ReadVariableOp:0$")
+    raw[f"{out_prefix}ln.b"] = _one(g, f"^{P}layer_normalization(_\\d+)?/add/ReadVariableOp:0$")
+    return H, dh, raw[cp + ".dw.w"].shape[0]
+
+
+def _count_blocks(g: Graph, stem: str) -> int:
+    idx = set()
+    rx = re.compile(f"^{stem}(\\d+)/")
+    for k in g.initializers:
+        m = rx.match(k)
+        if m:
+            idx.add(int(m.group(1)))
+    return len(idx)
+
+
+def import_encoder(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
+    """encoder.onnx -> (geometry, raw weights).  Graph = Melspectrogram -> ConvSubsampling -> N x ConformerBlock
+    (conformer_blocks.py:343-356)."""
+    g = load_graph(path)
+    w = _Walker(g)
+    raw: Dict[str, np.ndarray] = {}
+    real = _one(g, r"^melspectrogram/convolution/ReadVariableOp:0$")              # [513,1,1024,1] cos * hann
+    raw["fe.window"] = np.ascontiguousarray(real[0, 0, :, 0])                      # bin 0: cos(0) * w[n] = w[n]
+    raw["fe.mel"] = _one(g, r"^melspectrogram/Reshape_1:0$")
+    c1 = _one(g, r"^conv_subsampling/conv2d/Conv2D/ReadVariableOp:0$")             # OIHW [D,1,3,3]
+    c2 = _one(g, r"^conv_subsampling/conv2d_1/Conv2D/ReadVariableOp:0$")           # OIHW [D,D,3,3]
+    raw["sub.conv1.w"] = np.ascontiguousarray(c1.transpose(2, 3, 1, 0))            # HWIO
+    raw["sub.conv1.b"] = _one(g, r"^conv_subsampling/conv2d/BiasAdd/ReadVariableOp:0$")
+    raw["sub.conv2.w"] = np.ascontiguousarray(c2.transpose(2, 3, 1, 0))
+    raw["sub.conv2.b"] = _one(g, r"^conv_subsampling/conv2d_1/BiasAdd/ReadVariableOp:0$")
+    raw["sub.lin.w"] = _one(g, r"^conv_subsampling/dense/Tensordot/ReadVariableOp:0$")
+    raw["sub.lin.b"] = _one(g, r"^conv_subsampling/dense/BiasAdd/ReadVariableOp:0$")
+    D = raw["sub.lin.b"].shape[0]
+    nb = _count_blocks(g, "conformer_block_")
+    H = dh = K = 0
+    for i in range(nb):
+        H, dh, K = _import_block(w, f"conformer_block_{i}/", f"enc.{i}.", raw)
+    geo = ModelGeometry(dmodel=D, num_blocks=nb, num_heads=H, head_size=dh, kernel_size=K,
+                        ff_dim=raw["enc.0.ffn1.w1"].shape[1], n_mels=raw["fe.mel"].shape[1],
+                        n_dft=raw["fe.window"].shape[0])
+    return geo, raw
+
+
+def import_ctc_model(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
+    """ctc_model.onnx -> (geometry, raw weights).  Graph = Dense -> N x ConformerBlock -> Dense(V)
+    (conformer_blocks.py:419-424)."""
+    g = load_graph(path)
+    w = _Walker(g)
+    raw: Dict[str, np.ndarray] = {}
+    raw["ctc.fc.w"] = _one(g, r"^fully_connected/Tensordot/ReadVariableOp:0$")
+    raw["ctc.fc.b"] = _one(g, r"^fully_connected/BiasAdd/ReadVariableOp:0$")
+    raw["ctc.proj.w"] = _one(g, r"^dense(_\d+)?/Tensordot/ReadVariableOp:0$")
+    raw["ctc.proj.b"] = _one(g, r"^dense(_\d+)?/BiasAdd/ReadVariableOp:0$")
+    nb = _count_blocks(g, "decoder_conformer_block_")
+    H = dh = K = 0
+    for i in range(nb):
+        H, dh, K = _import_block(w, f"decoder_conformer_block_{i}/", f"ctc.blk{i}.", raw)
+    D = raw["ctc.proj.b"].shape[0]
+    geo = ModelGeometry(dmodel=D, num_blocks=nb, num_heads=H, head_size=dh, kernel_size=K,
+                        ff_dim=raw["ctc.blk0.ffn1.w1"].shape[1], vocab=raw["ctc.fc.b"].shape[0])
+    return geo, raw
+
+
+# --------------------------------------------------------------------------------------------------------
+# synthetic weights (ChunkConformer has no shipped weights; also used by unit tests)
+# --------------------------------------------------------------------------------------------------------
+def hann_periodic(n: int) -> np.ndarray:
+    """scipy/librosa get_window('hann', n, fftbins=True) (backend.py:58)."""
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)).astype(np.float32)
+
+
+def slaney_mel_l1(sr: int = 16000, n_fft: int = 1024, n_mels: int = 80) -> np.ndarray:
+    """Slaney-scale triangular filters, each L1-normalised (what the shipped ONNX holds).  [513, n_mels]"""
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        lin = f / (200.0 / 3)
+        logstep = np.log(6.4) / 27.0
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-9) / 1000.0) / logstep, lin)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        logstep = np.log(6.4) / 27.0
+        return np.where(m >= 15.0, 1000.0 * np.exp(logstep * (m - 15.0)), m * 200.0 / 3)
+
+    fft_f = np.linspace(0, sr / 2, n_fft // 2 + 1)
+    mel_f = mel_to_hz(np.linspace(hz_to_mel(0.0), hz_to_mel(sr / 2), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fft_f[None, :]
+    w = np.zeros((n_mels, n_fft // 2 + 1))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.maximum(0, np.minimum(lower, upper))
+    s = w.sum(axis=1, keepdims=True)
+    w = w / np.where(s > 0, s, 1.0)
+    return np.ascontiguousarray(w.T.astype(np.float32))
+
+
+def random_block(rng: np.random.Generator, prefix: str, D: int, H: int, dh: int, K: int, F: int,
+                 raw: Dict[str, np.ndarray], scale: float = 1.0):
+    def nrm(*shape, s):
+        return (rng.standard_normal(shape) * s * scale).astype(np.float32)
+
+    def lnp(name):
+        raw[name + ".g"] = (1.0 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+        raw[name + ".b"] = (0.05 * rng.standard_normal(D)).astype(np.float32)
+
+    for k in (1, 2):
+        p = f"{prefix}ffn{k}"
+        lnp(p + ".ln")
+        raw[p + ".w1"] = nrm(D, F, s=D ** -0.5)
+        raw[p + ".b1"] = nrm(F, s=0.1)
+        raw[p + ".w2"] = nrm(F, D, s=F ** -0.5)
+        raw[p + ".b2"] = nrm(D, s=0.1)
+    p = f"{prefix}mhsa"
+    lnp(p + ".ln")
+    for nm in ("wq", "wk", "wv"):
+        raw[f"{p}.{nm}"] = nrm(H, D, dh, s=D ** -0.5 * 1.5)
+    raw[p + ".wo"] = nrm(H, dh, D, s=(H * dh) ** -0.5)
+    raw[p + ".bo"] = nrm(D, s=0.1)
+    p = f"{prefix}conv"
+    lnp(p + ".ln")
+    raw[p + ".pw1.w"] = nrm(D, 2 * D, s=D ** -0.5)
+    raw[p + ".pw1.b"] = nrm(2 * D, s=0.1)
+    raw[p + ".dw.w"] = nrm(K, D, s=K ** -0.5)
+    raw[p + ".pw.w"] = nrm(D, 2 * D, s=D ** -0.5)
+    raw[p + ".pw.b"] = nrm(2 * D, s=0.1)
+    raw[p + ".bn.scale"] = (1.0 + 0.1 * rng.standard_normal(2 * D)).astype(np.float32)
+    raw[p + ".bn.shift"] = nrm(2 * D, s=0.1)
+    raw[p + ".pw2.w"] = nrm(2 * D, D, s=(2 * D) ** -0.5)
+    raw[p + ".pw2.b"] = nrm(D, s=0.1)
+    raw[f"{prefix}ln.g"] = (1.0 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    raw[f"{prefix}ln.b"] = (0.05 * rng.standard_normal(D)).astype(np.float32)
+
+
+def random_model(seed: int, dmodel: int = 144, num_blocks: int = 2, num_heads: int = 4, head_size: int = 36,
+                 kernel_size: int = 32, vocab: int = 1332, ctc_blocks: int = 1, n_mels: int = 80
+                 ) -> Tuple[ModelGeometry, Dict[str, np.ndarray], ModelGeometry, Dict[str, np.ndarray]]:
+    """Seeded random-init encoder + CTC decoder of the reference architecture (for tests and for configs whose
+    trained weights are not shipped)."""
+    rng = np.random.default_rng(seed)
+    D, F = dmodel, 4 * dmodel
+    enc: Dict[str, np.ndarray] = {}
+    enc["fe.window"] = hann_periodic(1024)
+    enc["fe.mel"] = slaney_mel_l1(16000, 1024, n_mels)
+    f2 = ((n_mels + 1) // 2 + 1) // 2
+    enc["sub.conv1.w"] = (rng.standard_normal((3, 3, 1, D)) * 0.05).astype(np.float32)
+    enc["sub.conv1.b"] = (rng.standard_normal(D) * 0.5).astype(np.float32)
+    enc["sub.conv2.w"] = (rng.standard_normal((3, 3, D, D)) * (9 * D) ** -0.5).astype(np.float32)
+    enc["sub.conv2.b"] = (rng.standard_normal(D) * 0.1).astype(np.float32)
+    enc["sub.lin.w"] = (rng.standard_normal((f2 * D, D)) * (f2 * D) ** -0.5).astype(np.float32)
+    enc["sub.lin.b"] = (rng.standard_normal(D) * 0.1).astype(np.float32)
+    for i in range(num_blocks):
+        random_block(rng, f"enc.{i}.", D, num_heads, head_size, kernel_size, F, enc)
+    geo_e = ModelGeometry(D, num_blocks, num_heads, head_size, kernel_size, F, n_mels=n_mels)
+    ctc: Dict[str, np.ndarray] = {}
+    ctc["ctc.proj.w"] = (rng.standard_normal((D, D)) * D ** -0.5).astype(np.float32)
+    ctc["ctc.proj.b"] = (rng.standard_normal(D) * 0.1).astype(np.float32)
+    for i in range(ctc_blocks):
+        random_block(rng, f"ctc.blk{i}.", D, num_heads, head_size, kernel_size, F, ctc)
+    ctc["ctc.fc.w"] = (rng.standard_normal((D, vocab)) * D ** -0.5 * 3.0).astype(np.float32)
+    ctc["ctc.fc.b"] = (rng.standard_normal(vocab) * 0.5).astype(np.float32)
+    geo_c = ModelGeometry(D, ctc_blocks, num_heads, head_size, kernel_size, F, vocab=vocab)
+    return geo_e, enc, geo_c, ctc
