@@ -1,0 +1,113 @@
+/* b200asr -- C ABI of the B200-native Conformer-CTC encode + decode path.
+ *
+ * Drop-in boundary.  The reference (Z-yq/TensorflowASR) has no plugin/FFI layer of its own: its
+ * deployment code drives three onnxruntime sessions.  Each entry point below stands in for one of those calls (or
+ * for one of the reference's native decoders) and keeps its tensor conventions: row-major, contiguous, float32
+ * activations, int32 token ids, blank = last class unless told otherwise.
+ *
+ *   b200asr_encode        <-> encoder session Run: "inputs" f32 [B,L,1] -> "Identity:0" f32 [B,T',D]
+ *                             Inference/CppInference/onnx/src/core/asr_session.cpp:77-97 (EncoderInference),
+ *                             Inference/PythonInference/asr/src/asr.py:34-39 (extract_feature), test_asr.py:191
+ *   b200asr_ctc_logits    <-> ctc_model session Run: "inputs" f32 [B,T',D] -> "Identity:0" f32 [B,T',V]
+ *                             asr_session.cpp:100-122 (CTCInference), asr.py:66-70, test_asr.py:193
+ *   b200asr_ctc_greedy    <-> std::vector<int> ctc_greedy_decoder(probs, blank_id, vocab_size)
+ *                             Inference/CppInference/onnx/src/core/ctc_greedy_decoder.h:4-43; asr.py:56-61;
+ *                             externals/ctc_decoders/ctc_greedy_decoder.cpp:4-45; tf.keras.backend.ctc_decode at
+ *                             test_asr.py:198 (pads with -1, honours input_length)
+ *   b200asr_ctc_beam      <-> ctc_beam_search_decoder / _batch(probs_seq, vocabulary, beam_size, cutoff_prob,
+ *                             cutoff_top_n, ext_scorer = nullptr)   externals/ctc_decoders/ctc_beam_search_decoder.h:26-60
+ *   b200asr_recognize*    <-> the whole offline_stt chain test_asr.py:186-200 (encoder -> ctc_model -> greedy ids)
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (then b200asr_last_error() describes it);
+ * no exception crosses the ABI.  `*_dev` pointers are CUDA device pointers owned by the caller, `*_host` pointers
+ * are host memory (pinned memory makes the copies asynchronous).  `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream); device-pointer entry points only enqueue work and never synchronise.  The library owns
+ * the weight copy and a workspace that grows on demand.  A handle is not thread safe; use one per host thread.
+ * There is no CPU fallback: creating a handle without a usable sm_100 GPU fails.
+ */
+#ifndef B200ASR_H_
+#define B200ASR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ASR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B200ASR_API __attribute__((visibility("default")))
+#else
+#define B200ASR_API
+#endif
+
+typedef struct b200asr_engine* b200asr_handle;
+
+/* arithmetic used by the GEMM-shaped ops (everything else is always fp32) */
+enum { B200ASR_PRECISION_TF32 = 0, /* tcgen05 tensor cores, tf32 inputs, fp32 accumulate */
+       B200ASR_PRECISION_FP32 = 1  /* CUDA-core fp32 (exact mode, used as on-device checker) */ };
+
+/* Geometry = the reference's model_config / speech_config keys (asr/configs/conformerS.yml, am_data.yml). */
+typedef struct {
+  int32_t abi_version;        /* B200ASR_ABI_VERSION */
+  /* encoder: model_config.{dmodel,num_blocks,num_heads,head_size,kernel_size}, ff = 4*dmodel */
+  int32_t dmodel, num_blocks, num_heads, head_size, kernel_size, ff_dim;
+  /* CTC decoder: model_config.ctcdecoder_{num_blocks,kernel_size}; vocab = classes incl. blank */
+  int32_t ctc_blocks, ctc_kernel_size, vocab;
+  /* frontend: speech_config.{num_feature_bins, sample_rate*stride_ms/1000}; n_dft fixed to 1024 by the reference */
+  int32_t n_mels, n_dft, hop;
+  float ln_eps;               /* Keras LayerNormalization default 1e-3 */
+  /* block streaming (StreamingConformerEncoder, conformer_blocks.py:567-594): >0 = encode independent chunks of this
+     many samples (speech_config.streaming_bucket * sample_rate); 0 = offline */
+  int32_t chunk_samples;
+  int32_t precision;          /* B200ASR_PRECISION_* */
+  int32_t use_cuda_graph;     /* 1 = capture each (shape, pointer set) once and replay */
+  int32_t reserved[8];
+} b200asr_config;
+
+/* Weight blob: produced by tensorflowasr_b200.weights.pack_for_device() (see weights.py for the tensor list).
+ *   char magic[8] = "B2ASRW01"; uint32 n_entries; uint32 pad;
+ *   n_entries x { char name[48]; uint64 byte_offset; uint64 numel; }   (float32 tensors, offsets 128-byte aligned)
+ */
+B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const b200asr_config* cfg, int device,
+                   b200asr_handle* out);
+B200ASR_API int b200asr_destroy(b200asr_handle h);
+B200ASR_API const char* b200asr_last_error(b200asr_handle h /* may be NULL: error of the failed create on this thread */);
+B200ASR_API int b200asr_abi_version(void);
+
+/* T' (encoder frames) produced for L samples: two 'same' stride-2 convs over ceil(L/hop) mel frames. */
+B200ASR_API int b200asr_out_frames(b200asr_handle h, int num_samples);
+/* Pre-size the workspace for batches up to (B, L) so later calls never allocate. */
+B200ASR_API int b200asr_reserve(b200asr_handle h, int B, int L);
+
+B200ASR_API int b200asr_encode(b200asr_handle h, const float* wav_dev /*[B,L]*/, int B, int L, float* enc_dev /*[B,T',D]*/,
+                   void* stream);
+/* mel features only ([B, ceil(L/hop), n_mels]) -- the Melspectrogram layer output (time_frequency.py:173-189) */
+B200ASR_API int b200asr_mel(b200asr_handle h, const float* wav_dev, int B, int L, float* mel_dev, void* stream);
+B200ASR_API int b200asr_ctc_logits(b200asr_handle h, const float* enc_dev /*[B,T',D]*/, int B, int Tp, float* logits_dev /*[B,T',V]*/,
+                       void* stream);
+/* lengths_dev may be NULL (= all Tp).  ids_dev [B,Tp] is padded with -1, out_len_dev [B]. */
+B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V,
+                       int blank, int32_t* ids_dev, int32_t* out_len_dev, void* stream);
+/* Prefix beam search without external scorer.  ids_dev [B,beam,Tp] (-1 padded), out_len_dev [B,beam],
+ * scores_dev [B,beam] (log prob, descending).  logits are softmax-normalised inside. */
+B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V,
+                     int blank, int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev,
+                     float* scores_dev, void* stream);
+
+/* wav -> greedy token ids in one call, device buffers. */
+B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev /*[B,T']*/,
+                      int32_t* out_len_dev /*[B]*/, void* stream);
+/* Same with HOST buffers: H2D of the waveform, compute, D2H of ids + lengths, stream-synchronised on return. */
+B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host,
+                           int32_t* out_len_host, void* stream);
+
+/* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
+B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ASR_H_ */

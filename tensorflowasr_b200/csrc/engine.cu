@@ -1,0 +1,674 @@
+// b200asr engine: weight residency, workspace, and the launch schedule of the Conformer-CTC path behind the
+// C ABI declared in include/b200asr.h.  No CPU fallback: creation fails without a usable CUDA device.
+#include "../../include/b200asr.h"
+#include "kernels.cuh"
+#include "gemm_tc.cuh"
+
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace b200asr {
+thread_local char g_errbuf[512] = {0};
+}
+
+using namespace b200asr;
+
+namespace {
+
+struct BlobEntry {
+  char name[48];
+  uint64_t offset;
+  uint64_t numel;
+};
+
+struct LNW { const float *g, *b; };
+struct FFNW { LNW ln; const float *w1, *b1, *w2, *b2; };
+struct MHSAW { LNW ln; const float *wqkv, *wo, *bo; };
+struct ConvW { LNW ln; const float *pw1w, *pw1b, *dww, *pww, *pwb, *pw2w, *pw2b; };
+struct BlockW { FFNW ffn1, ffn2; MHSAW mhsa; ConvW conv; LNW ln; int kernel_size; };
+
+struct Workspace {
+  float* base = nullptr;
+  size_t bytes = 0;
+};
+
+struct GraphKey {
+  int kind, B, L;
+  const void *p0, *p1, *p2;
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+
+}  // namespace
+
+struct b200asr_engine {
+  b200asr_config cfg;
+  int device = 0;
+  char* blob_dev = nullptr;
+  std::map<std::string, std::pair<const float*, uint64_t>> tensors;
+  // frontend
+  const float *window = nullptr, *melw = nullptr;
+  float2* twiddle = nullptr;
+  int *mel_lo = nullptr, *mel_hi = nullptr;
+  // subsampling
+  const float *c1w, *c1b, *c2w, *c2b, *linw, *linb;
+  std::vector<BlockW> enc_blocks, ctc_blocks;
+  const float *ctc_projw, *ctc_projb, *ctc_fcw, *ctc_fcb;
+  int F1 = 0, F2 = 0;  // mel bins after conv1 / conv2
+  Workspace ws;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int64_t> graph_launches;
+  int64_t launches = 0;
+  std::string err;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  TcContext tc;  // tcgen05 GEMM state (tensor-map encoder entry point etc.)
+};
+
+namespace {
+
+int fail(b200asr_handle h, const char* msg) {
+  if (h) h->err = msg;
+  snprintf(g_errbuf, sizeof(g_errbuf), "%s", msg);
+  return 1;
+}
+int fail_cuda(b200asr_handle h) {
+  if (h) h->err = g_errbuf;
+  return 1;
+}
+
+#define ENG_CUDA(h, expr)                                                                                  \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) {                                                                               \
+      snprintf(g_errbuf, sizeof(g_errbuf), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return fail_cuda(h);                                                                                 \
+    }                                                                                                      \
+  } while (0)
+#define ENG_TRY(h, expr)           \
+  do {                             \
+    if ((expr) != 0) return fail_cuda(h); \
+  } while (0)
+
+const float* lookup(b200asr_handle h, const std::string& name, uint64_t expect_numel, bool* ok) {
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "weight blob: tensor '%s' missing", name.c_str());
+    *ok = false;
+    return nullptr;
+  }
+  if (expect_numel && it->second.second != expect_numel) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "weight blob: tensor '%s' has %llu elements, expected %llu", name.c_str(),
+             (unsigned long long)it->second.second, (unsigned long long)expect_numel);
+    *ok = false;
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+bool load_block(b200asr_handle h, const std::string& p, int D, int F, int H, int dh, int K, BlockW* w) {
+  bool ok = true;
+  auto L = [&](const std::string& n, uint64_t numel) { return lookup(h, p + n, numel, &ok); };
+  const uint64_t uD = D, uF = F;
+  FFNW* ff[2] = {&w->ffn1, &w->ffn2};
+  for (int i = 0; i < 2 && ok; ++i) {
+    const std::string q = std::string("ffn") + char('1' + i);
+    ff[i]->ln.g = L(q + ".ln.g", uD);
+    ff[i]->ln.b = L(q + ".ln.b", uD);
+    ff[i]->w1 = L(q + ".w1", uF * uD);
+    ff[i]->b1 = L(q + ".b1", uF);
+    ff[i]->w2 = L(q + ".w2", uD * uF);
+    ff[i]->b2 = L(q + ".b2", uD);
+  }
+  w->mhsa.ln.g = L("mhsa.ln.g", uD);
+  w->mhsa.ln.b = L("mhsa.ln.b", uD);
+  w->mhsa.wqkv = L("mhsa.wqkv", 3ull * H * dh * uD);
+  w->mhsa.wo = L("mhsa.wo", uD * H * dh);
+  w->mhsa.bo = L("mhsa.bo", uD);
+  w->conv.ln.g = L("conv.ln.g", uD);
+  w->conv.ln.b = L("conv.ln.b", uD);
+  w->conv.pw1w = L("conv.pw1.w", 2 * uD * uD);
+  w->conv.pw1b = L("conv.pw1.b", 2 * uD);
+  w->conv.dww = L("conv.dw.w", (uint64_t)K * uD);
+  w->conv.pww = L("conv.pw.w", 2 * uD * uD);
+  w->conv.pwb = L("conv.pw.b", 2 * uD);
+  w->conv.pw2w = L("conv.pw2.w", 2 * uD * uD);
+  w->conv.pw2b = L("conv.pw2.b", uD);
+  w->ln.g = L("ln.g", uD);
+  w->ln.b = L("ln.b", uD);
+  w->kernel_size = K;
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct Shapes {
+  int B, L, T, pad_left, T1, T2, pt1, pf1, pt2, pf2, M;
+};
+
+Shapes shapes_for(b200asr_handle h, int B, int L) {
+  Shapes s;
+  const b200asr_config& c = h->cfg;
+  s.B = B;
+  s.L = L;
+  SamePad fp = same_pad(L, c.n_dft, c.hop);
+  s.T = fp.out;
+  s.pad_left = fp.before;
+  SamePad t1 = same_pad(s.T, 3, 2), f1 = same_pad(c.n_mels, 3, 2);
+  s.T1 = t1.out; s.pt1 = t1.before; s.pf1 = f1.before;
+  SamePad t2 = same_pad(s.T1, 3, 2), f2 = same_pad(h->F1, 3, 2);
+  s.T2 = t2.out; s.pt2 = t2.before; s.pf2 = f2.before;
+  s.M = B * s.T2;
+  return s;
+}
+
+constexpr int kPowerStride = 520;
+
+struct Buffers {
+  float *power, *mel, *c1, *c2, *x, *xn, *h, *att, *g, *logits;
+  unsigned int* pmax;
+  int *am, *ids, *lens;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t carve(b200asr_handle h, const Shapes& s, Buffers* b, char* base) {
+  const b200asr_config& c = h->cfg;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(nfloat * sizeof(float), 256);
+    return reinterpret_cast<float*>(p);
+  };
+  const size_t D = c.dmodel, M = s.M;
+  const size_t wide = (size_t)std::max(std::max(c.ff_dim, 3 * c.num_heads * c.head_size), 2 * c.dmodel);
+  b->power = take((size_t)s.B * s.T * kPowerStride);
+  b->mel = take((size_t)s.B * s.T * c.n_mels);
+  b->c1 = take((size_t)s.B * s.T1 * h->F1 * D);
+  b->c2 = take((size_t)s.B * s.T2 * h->F2 * D);
+  b->x = take(M * D);
+  b->xn = take(M * D);
+  b->h = take(M * wide);
+  b->att = take(M * D);
+  b->g = take(M * D);
+  b->logits = take(M * (size_t)std::max(c.vocab, 1));
+  b->pmax = reinterpret_cast<unsigned int*>(take(s.B));
+  b->am = reinterpret_cast<int*>(take(M));
+  b->ids = reinterpret_cast<int*>(take(M));
+  b->lens = reinterpret_cast<int*>(take(s.B));
+  return off;
+}
+
+int ensure_workspace(b200asr_handle h, const Shapes& s, Buffers* b) {
+  size_t need = carve(h, s, b, nullptr);
+  if (need > h->ws.bytes) {
+    // growing the workspace invalidates captured graphs (they hold the old addresses)
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    h->graph_launches.clear();
+    ENG_CUDA(h, cudaDeviceSynchronize());
+    if (h->ws.base) ENG_CUDA(h, cudaFree(h->ws.base));
+    h->ws.base = nullptr;
+    h->ws.bytes = 0;
+    ENG_CUDA(h, cudaMalloc(&h->ws.base, need));
+    h->ws.bytes = need;
+  }
+  carve(h, s, b, reinterpret_cast<char*>(h->ws.base));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ schedule
+struct Ctx {
+  b200asr_handle h;
+  cudaStream_t s;
+};
+
+int gemm(Ctx& c, const float* A, int lda, const float* W, const float* bias, const float* resid, float alpha, float* C,
+         int ldc, int M, int N, int K, int epi) {
+  GemmParams p{};
+  p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C;
+  p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.alpha = alpha; p.a_mode = 0;
+  c.h->launches++;
+  if (c.h->cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(p, epi)) return launch_gemm_tc(c.h->tc, p, epi, c.s);
+  return launch_gemm_simt(p, epi, c.s);
+}
+
+int run_block(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, int F, int H, int dh, float eps) {
+  const int M = B * T;
+  const FFNW* ff[2] = {&w.ffn1, &w.ffn2};
+  auto ffn = [&](const FFNW& f) -> int {
+    c.h->launches++;
+    if (launch_layernorm(b.x, f.ln.g, f.ln.b, b.xn, M, D, eps, c.s)) return 1;
+    if (gemm(c, b.xn, D, f.w1, f.b1, nullptr, 0.f, b.h, F, M, F, D, EPI_BIAS_SWISH)) return 1;
+    if (gemm(c, b.h, F, f.w2, f.b2, b.x, 0.5f, b.x, D, M, D, F, EPI_RESID)) return 1;
+    return 0;
+  };
+  if (ffn(*ff[0])) return 1;
+  // MHSA
+  c.h->launches++;
+  if (launch_layernorm(b.x, w.mhsa.ln.g, w.mhsa.ln.b, b.xn, M, D, eps, c.s)) return 1;
+  const int HD = H * dh;
+  if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
+  AttnParams ap{};
+  ap.qkv = b.h; ap.out = b.att; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = -1; ap.win_back = 0;
+  c.h->launches++;
+  if (launch_attention(ap, c.s)) return 1;
+  if (gemm(c, b.att, HD, w.mhsa.wo, w.mhsa.bo, b.x, 1.0f, b.x, D, M, D, HD, EPI_RESID)) return 1;
+  // conv module
+  c.h->launches++;
+  if (launch_layernorm(b.x, w.conv.ln.g, w.conv.ln.b, b.xn, M, D, eps, c.s)) return 1;
+  if (gemm(c, b.xn, D, w.conv.pw1w, w.conv.pw1b, nullptr, 0.f, b.g, D, M, 2 * D, D, EPI_GLU)) return 1;
+  DwConvParams dp{};
+  dp.x = b.g; dp.w = w.conv.dww; dp.y = b.att; dp.B = B; dp.T = T; dp.D = D; dp.K = w.kernel_size;
+  dp.pad_left = same_pad(T, w.kernel_size, 1).before;
+  c.h->launches++;
+  if (launch_dwconv(dp, c.s)) return 1;
+  if (gemm(c, b.att, D, w.conv.pww, w.conv.pwb, nullptr, 0.f, b.h, 2 * D, M, 2 * D, D, EPI_BIAS_SWISH)) return 1;
+  if (gemm(c, b.h, 2 * D, w.conv.pw2w, w.conv.pw2b, b.x, 1.0f, b.x, D, M, D, 2 * D, EPI_RESID)) return 1;
+  if (ffn(*ff[1])) return 1;
+  c.h->launches++;
+  if (launch_layernorm(b.x, w.ln.g, w.ln.b, b.x, M, D, eps, c.s)) return 1;
+  return 0;
+}
+
+int run_frontend(Ctx& c, const float* wav, const Shapes& s, const Buffers& b, float* mel_out) {
+  b200asr_handle h = c.h;
+  FrontendParams fp{};
+  fp.wav = wav; fp.window = h->window; fp.twiddle = h->twiddle; fp.melw = h->melw; fp.mel_lo = h->mel_lo;
+  fp.mel_hi = h->mel_hi; fp.power = b.power; fp.pmax = b.pmax; fp.mel = mel_out; fp.B = s.B; fp.L = s.L; fp.T = s.T;
+  fp.pad_left = s.pad_left; fp.hop = h->cfg.hop; fp.power_stride = kPowerStride; fp.n_mels = h->cfg.n_mels; fp.mode = 0;
+  h->launches += 3;
+  return launch_frontend(fp, c.s);
+}
+
+// wav [B, L] -> b.x [B*T2, D]
+int run_encoder(Ctx& c, const float* wav, const Shapes& s, const Buffers& b) {
+  b200asr_handle h = c.h;
+  const b200asr_config& cfg = h->cfg;
+  const int D = cfg.dmodel;
+  if (run_frontend(c, wav, s, b, b.mel)) return 1;
+  Conv1Params c1{};
+  c1.mel = b.mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
+  c1.F1 = h->F1; c1.D = D; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
+  h->launches++;
+  if (launch_conv1(c1, c.s)) return 1;
+  GemmParams g{};
+  g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = D; g.K = 9 * D; g.lda = 0; g.ldc = D;
+  g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = D; g.pad_t = s.pt2; g.pad_f = s.pf2;
+  h->launches++;
+  if (cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(g, EPI_BIAS_RELU)) {
+    if (launch_gemm_tc(h->tc, g, EPI_BIAS_RELU, c.s)) return 1;
+  } else {
+    if (launch_gemm_simt(g, EPI_BIAS_RELU, c.s)) return 1;
+  }
+  if (gemm(c, b.c2, h->F2 * D, h->linw, h->linb, nullptr, 0.f, b.x, D, s.M, D, h->F2 * D, EPI_BIAS)) return 1;
+  for (const BlockW& w : h->enc_blocks)
+    if (run_block(c, w, b, s.B, s.T2, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps)) return 1;
+  return 0;
+}
+
+// enc [B*Tp, D] -> logits [B*Tp, V]   (uses b.x as the running activation; enc may alias b.x's source)
+int run_ctc(Ctx& c, const float* enc, int B, int Tp, const Buffers& b, float* logits) {
+  b200asr_handle h = c.h;
+  const b200asr_config& cfg = h->cfg;
+  const int D = cfg.dmodel, M = B * Tp;
+  // the block schedule runs in place on its `x` buffer; when the input *is* b.x, project into b.xn and swap roles
+  Buffers bb = b;
+  if (enc == b.x) std::swap(bb.x, bb.xn);
+  if (gemm(c, enc, D, h->ctc_projw, h->ctc_projb, nullptr, 0.f, bb.x, D, M, D, D, EPI_BIAS)) return 1;
+  for (const BlockW& w : h->ctc_blocks)
+    if (run_block(c, w, bb, B, Tp, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps)) return 1;
+  if (gemm(c, bb.x, D, h->ctc_fcw, h->ctc_fcb, nullptr, 0.f, logits, cfg.vocab, M, cfg.vocab, D, EPI_BIAS)) return 1;
+  return 0;
+}
+
+void effective_batch(b200asr_handle h, int* B, int* L) {
+  const int cs = h->cfg.chunk_samples;
+  if (cs > 0 && *L > cs && (*L % cs) == 0) {
+    *B = *B * (*L / cs);
+    *L = cs;
+  }
+}
+
+// Run `body(stream)` either directly or through a cached CUDA graph keyed on shapes + pointers.  Graphs cannot be
+// captured on the legacy default stream, so calls that arrive on it are bridged (event in / event out) onto a
+// private stream; ordering with respect to the caller's stream is preserved.
+template <class Body>
+int with_graph(b200asr_handle h, cudaStream_t s, const GraphKey& key, Body body) {
+  if (!h->cfg.use_cuda_graph) return body(s);
+  cudaStream_t rs = s;
+  const bool bridged = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
+  if (bridged) {
+    if (!h->own_stream) {
+      ENG_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+      ENG_CUDA(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+      ENG_CUDA(h, cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    rs = h->own_stream;
+    ENG_CUDA(h, cudaEventRecord(h->ev_in, s));
+    ENG_CUDA(h, cudaStreamWaitEvent(rs, h->ev_in, 0));
+  }
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    if (h->graphs.size() >= 32) {
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+      h->graphs.clear();
+      h->graph_launches.clear();
+    }
+    cudaGraph_t graph = nullptr;
+    const int64_t before = h->launches;
+    ENG_CUDA(h, cudaStreamBeginCapture(rs, cudaStreamCaptureModeThreadLocal));
+    int rc = body(rs);
+    h->graph_launches[key] = h->launches - before;
+    h->launches = before;
+    cudaError_t e = cudaStreamEndCapture(rs, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) {
+      snprintf(g_errbuf, sizeof(g_errbuf), "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      return fail_cuda(h);
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      snprintf(g_errbuf, sizeof(g_errbuf), "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+      return fail_cuda(h);
+    }
+    it = h->graphs.emplace(key, exec).first;
+  }
+  ENG_CUDA(h, cudaGraphLaunch(it->second, rs));
+  h->launches += h->graph_launches[key];
+  if (bridged) {
+    ENG_CUDA(h, cudaEventRecord(h->ev_out, rs));
+    ENG_CUDA(h, cudaStreamWaitEvent(s, h->ev_out, 0));
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================== C ABI
+extern "C" {
+
+B200ASR_API int b200asr_abi_version(void) { return B200ASR_ABI_VERSION; }
+
+B200ASR_API const char* b200asr_last_error(b200asr_handle h) { return h ? h->err.c_str() : g_errbuf; }
+
+B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const b200asr_config* cfg, int device, b200asr_handle* out) {
+  if (!weight_blob || !cfg || !out) return fail(nullptr, "b200asr_create: null argument");
+  if (cfg->abi_version != B200ASR_ABI_VERSION) return fail(nullptr, "b200asr_create: ABI version mismatch");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, "b200asr_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, "b200asr_create: bad device index");
+  cudaDeviceProp prop;
+  ENG_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: device %d is sm_%d%d; this build targets sm_100a (B200) only", device,
+             prop.major, prop.minor);
+    return 1;
+  }
+  ENG_CUDA(nullptr, cudaSetDevice(device));
+  if (blob_bytes < 16 || memcmp(weight_blob, "B2ASRW01", 8) != 0) return fail(nullptr, "b200asr_create: bad weight blob magic");
+  const char* hb = static_cast<const char*>(weight_blob);
+  uint32_t n_entries;
+  memcpy(&n_entries, hb + 8, 4);
+  const size_t table_end = 16 + (size_t)n_entries * sizeof(BlobEntry);
+  if (table_end > blob_bytes) return fail(nullptr, "b200asr_create: truncated weight blob");
+
+  b200asr_engine* h = new b200asr_engine();
+  h->cfg = *cfg;
+  h->device = device;
+  auto bail = [&](int) {
+    std::string e = g_errbuf;
+    b200asr_destroy(h);
+    snprintf(g_errbuf, sizeof(g_errbuf), "%s", e.c_str());
+    return 1;
+  };
+  if (cudaMalloc(&h->blob_dev, blob_bytes) != cudaSuccess ||
+      cudaMemcpy(h->blob_dev, weight_blob, blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: cannot place %zu weight bytes on device", blob_bytes);
+    return bail(1);
+  }
+  for (uint32_t i = 0; i < n_entries; ++i) {
+    BlobEntry e;
+    memcpy(&e, hb + 16 + (size_t)i * sizeof(BlobEntry), sizeof(BlobEntry));
+    e.name[47] = 0;
+    if (e.offset % 128 != 0 || e.offset + e.numel * 4 > blob_bytes) {
+      snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: entry '%s' out of bounds / misaligned", e.name);
+      return bail(1);
+    }
+    h->tensors[e.name] = {reinterpret_cast<const float*>(h->blob_dev + e.offset), e.numel};
+  }
+  const b200asr_config& c = h->cfg;
+  if (c.n_dft != 1024) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: n_dft must be 1024 (reference hard-codes it)"); return bail(1); }
+  if (c.dmodel % 16 != 0 || c.dmodel > 512) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: dmodel must be a multiple of 16, <= 512"); return bail(1); }
+  const int D = c.dmodel, nb = c.n_dft / 2 + 1;
+  h->F1 = same_pad(c.n_mels, 3, 2).out;
+  h->F2 = same_pad(h->F1, 3, 2).out;
+  bool ok = true;
+  h->window = lookup(h, "fe.window", c.n_dft, &ok);
+  h->melw = ok ? lookup(h, "fe.mel", (uint64_t)nb * c.n_mels, &ok) : nullptr;
+  h->c1w = ok ? lookup(h, "sub.conv1.w", 9ull * D, &ok) : nullptr;
+  h->c1b = ok ? lookup(h, "sub.conv1.b", D, &ok) : nullptr;
+  h->c2w = ok ? lookup(h, "sub.conv2.w", 9ull * D * D, &ok) : nullptr;
+  h->c2b = ok ? lookup(h, "sub.conv2.b", D, &ok) : nullptr;
+  h->linw = ok ? lookup(h, "sub.lin.w", (uint64_t)h->F2 * D * D, &ok) : nullptr;
+  h->linb = ok ? lookup(h, "sub.lin.b", D, &ok) : nullptr;
+  if (!ok) return bail(1);
+  h->enc_blocks.resize(c.num_blocks);
+  for (int i = 0; i < c.num_blocks; ++i)
+    if (!load_block(h, "enc." + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.kernel_size, &h->enc_blocks[i]))
+      return bail(1);
+  if (c.vocab > 0) {
+    h->ctc_projw = lookup(h, "ctc.proj.w", (uint64_t)D * D, &ok);
+    h->ctc_projb = ok ? lookup(h, "ctc.proj.b", D, &ok) : nullptr;
+    h->ctc_fcw = ok ? lookup(h, "ctc.fc.w", (uint64_t)c.vocab * D, &ok) : nullptr;
+    h->ctc_fcb = ok ? lookup(h, "ctc.fc.b", c.vocab, &ok) : nullptr;
+    if (!ok) return bail(1);
+    h->ctc_blocks.resize(c.ctc_blocks);
+    for (int i = 0; i < c.ctc_blocks; ++i)
+      if (!load_block(h, "ctc.blk" + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.ctc_kernel_size,
+                      &h->ctc_blocks[i]))
+        return bail(1);
+  }
+  // FFT twiddles exp(-2 pi i m / 1024), rounded once from double
+  std::vector<float2> tw(c.n_dft);
+  for (int m = 0; m < c.n_dft; ++m) {
+    const double a = -2.0 * M_PI * (double)m / (double)c.n_dft;
+    tw[m] = make_float2((float)cos(a), (float)sin(a));
+  }
+  // sparse extent of each mel filter (the reference multiplies by the dense matrix; zeros contribute nothing)
+  const float* melw_host = nullptr;
+  for (uint32_t i = 0; i < n_entries; ++i) {
+    BlobEntry e;
+    memcpy(&e, hb + 16 + (size_t)i * sizeof(BlobEntry), sizeof(BlobEntry));
+    e.name[47] = 0;
+    if (strcmp(e.name, "fe.mel") == 0) melw_host = reinterpret_cast<const float*>(hb + e.offset);
+  }
+  std::vector<int> lo(c.n_mels, 0), hi(c.n_mels, 0);
+  for (int m = 0; m < c.n_mels; ++m) {
+    int l = nb, r = 0;
+    for (int k = 0; k < nb; ++k)
+      if (melw_host[(size_t)k * c.n_mels + m] != 0.0f) {
+        l = std::min(l, k);
+        r = std::max(r, k + 1);
+      }
+    if (l >= r) l = r = 0;
+    lo[m] = l;
+    hi[m] = r;
+  }
+  if (cudaMalloc(&h->twiddle, sizeof(float2) * c.n_dft) != cudaSuccess ||
+      cudaMalloc(&h->mel_lo, sizeof(int) * c.n_mels) != cudaSuccess ||
+      cudaMalloc(&h->mel_hi, sizeof(int) * c.n_mels) != cudaSuccess ||
+      cudaMemcpy(h->twiddle, tw.data(), sizeof(float2) * c.n_dft, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->mel_lo, lo.data(), sizeof(int) * c.n_mels, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->mel_hi, hi.data(), sizeof(int) * c.n_mels, cudaMemcpyHostToDevice) != cudaSuccess) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: device allocation of frontend tables failed");
+    return bail(1);
+  }
+  if (tc_init(&h->tc) != 0) return bail(1);
+  *out = h;
+  return 0;
+}
+
+B200ASR_API int b200asr_destroy(b200asr_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->blob_dev) cudaFree(h->blob_dev);
+  if (h->twiddle) cudaFree(h->twiddle);
+  if (h->mel_lo) cudaFree(h->mel_lo);
+  if (h->mel_hi) cudaFree(h->mel_hi);
+  if (h->ws.base) cudaFree(h->ws.base);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  delete h;
+  return 0;
+}
+
+B200ASR_API int b200asr_out_frames(b200asr_handle h, int num_samples) {
+  if (!h || num_samples <= 0) return 0;
+  int B = 1, L = num_samples;
+  effective_batch(h, &B, &L);
+  return shapes_for(h, 1, L).T2 * B;
+}
+
+B200ASR_API int b200asr_reserve(b200asr_handle h, int B, int L) {
+  if (!h) return 1;
+  if (B <= 0 || L <= 0) return fail(h, "b200asr_reserve: B and L must be positive");
+  effective_batch(h, &B, &L);
+  Buffers b;
+  Shapes s = shapes_for(h, B, L);
+  return ensure_workspace(h, s, &b);
+}
+
+B200ASR_API int64_t b200asr_launch_count(b200asr_handle h) { return h ? h->launches : 0; }
+
+B200ASR_API int b200asr_mel(b200asr_handle h, const float* wav_dev, int B, int L, float* mel_dev, void* stream) {
+  if (!h) return 1;
+  if (B < 0 || L <= 0 || !wav_dev || !mel_dev) return fail(h, "b200asr_mel: bad arguments");
+  if (B == 0) return 0;
+  effective_batch(h, &B, &L);
+  Shapes s = shapes_for(h, B, L);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  Ctx c{h, static_cast<cudaStream_t>(stream)};
+  ENG_TRY(h, run_frontend(c, wav_dev, s, b, mel_dev));
+  return 0;
+}
+
+B200ASR_API int b200asr_encode(b200asr_handle h, const float* wav_dev, int B, int L, float* enc_dev, void* stream) {
+  if (!h) return 1;
+  if (B < 0 || L <= 0 || !wav_dev || !enc_dev) return fail(h, "b200asr_encode: bad arguments");
+  if (B == 0) return 0;
+  effective_batch(h, &B, &L);
+  Shapes s = shapes_for(h, B, L);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GraphKey key{};
+  key.kind = 1; key.B = B; key.L = L; key.p0 = wav_dev; key.p1 = enc_dev;
+  return with_graph(h, st, key, [&](cudaStream_t st) -> int {
+    Ctx c{h, st};
+    ENG_TRY(h, run_encoder(c, wav_dev, s, b));
+    ENG_CUDA(h, cudaMemcpyAsync(enc_dev, b.x, sizeof(float) * (size_t)s.M * h->cfg.dmodel, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  });
+}
+
+B200ASR_API int b200asr_ctc_logits(b200asr_handle h, const float* enc_dev, int B, int Tp, float* logits_dev, void* stream) {
+  if (!h) return 1;
+  if (h->cfg.vocab <= 0) return fail(h, "b200asr_ctc_logits: engine was created without a CTC decoder");
+  if (B < 0 || Tp < 0 || !enc_dev || !logits_dev) return fail(h, "b200asr_ctc_logits: bad arguments");
+  if (B == 0 || Tp == 0) return 0;
+  // workspace sized through an equivalent (B, L): T2 = Tp  <=  L = Tp * 4 * hop
+  Shapes s = shapes_for(h, B, Tp * 4 * h->cfg.hop);
+  if (s.T2 != Tp) return fail(h, "b200asr_ctc_logits: internal shape inference mismatch");
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GraphKey key{};
+  key.kind = 2; key.B = B; key.L = Tp; key.p0 = enc_dev; key.p1 = logits_dev;
+  return with_graph(h, st, key, [&](cudaStream_t st) -> int {
+    Ctx c{h, st};
+    ENG_TRY(h, run_ctc(c, enc_dev, B, Tp, b, logits_dev));
+    return 0;
+  });
+}
+
+B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank,
+                       int32_t* ids_dev, int32_t* out_len_dev, void* stream) {
+  if (!h) return 1;
+  if (B < 0 || Tp < 0 || V <= 0 || !ids_dev || !out_len_dev || (!logits_dev && B * Tp > 0))
+    return fail(h, "b200asr_ctc_greedy: bad arguments");
+  if (B == 0) return 0;
+  Shapes s = shapes_for(h, B, std::max(Tp, 1) * 4 * h->cfg.hop);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  h->launches += 2;
+  ENG_TRY(h, launch_ctc_greedy(logits_dev, lengths_dev, B, Tp, V, blank, b.am, ids_dev, out_len_dev,
+                               static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev, int32_t* out_len_dev,
+                      void* stream) {
+  if (!h) return 1;
+  if (h->cfg.vocab <= 0) return fail(h, "b200asr_recognize: engine was created without a CTC decoder");
+  if (B < 0 || L <= 0 || !wav_dev || !ids_dev || !out_len_dev) return fail(h, "b200asr_recognize: bad arguments");
+  if (B == 0) return 0;
+  const int B0 = B;
+  effective_batch(h, &B, &L);
+  Shapes s = shapes_for(h, B, L);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Tp = s.M / B0;  // frames per original utterance (chunks concatenated in time)
+  GraphKey key{};
+  key.kind = 3; key.B = B; key.L = L; key.p0 = wav_dev; key.p1 = ids_dev; key.p2 = out_len_dev;
+  return with_graph(h, st, key, [&](cudaStream_t st) -> int {
+    Ctx c{h, st};
+    ENG_TRY(h, run_encoder(c, wav_dev, s, b));
+    // the CTC decoder sees whole utterances: [B0, Tp, D]; its input is the encoder output held in b.x
+    ENG_TRY(h, run_ctc(c, b.x, B0, Tp, b, b.logits));
+    h->launches += 2;
+    ENG_TRY(h, launch_ctc_greedy(b.logits, nullptr, B0, Tp, h->cfg.vocab, h->cfg.vocab - 1, b.am, ids_dev, out_len_dev, st));
+    return 0;
+  });
+}
+
+B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host, int32_t* out_len_host,
+                           void* stream) {
+  if (!h) return 1;
+  if (B < 0 || L <= 0 || !wav_host || !ids_host || !out_len_host) return fail(h, "b200asr_recognize_host: bad arguments");
+  if (B == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // staging buffers live at the end of a workspace sized for this shape
+  int Be = B, Le = L;
+  effective_batch(h, &Be, &Le);
+  Shapes s = shapes_for(h, Be, Le);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  const int Tp = s.M / B;
+  // reuse b.power as the device-side waveform staging area is not possible (the frontend writes it); b.c2 is free
+  // until conv2 runs, but the waveform must outlive the STFT only -- use b.att (M*D floats) if large enough, else c2.
+  float* wav_dev = b.c2;
+  const size_t need = (size_t)B * L;
+  const size_t have = (size_t)s.B * s.T2 * h->F2 * h->cfg.dmodel;
+  if (need > have) return fail(h, "b200asr_recognize_host: staging area too small for this waveform");
+  ENG_CUDA(h, cudaMemcpyAsync(wav_dev, wav_host, sizeof(float) * need, cudaMemcpyHostToDevice, st));
+  if (b200asr_recognize(h, wav_dev, B, L, b.ids, b.lens, st)) return 1;
+  ENG_CUDA(h, cudaMemcpyAsync(ids_host, b.ids, sizeof(int32_t) * (size_t)B * Tp, cudaMemcpyDeviceToHost, st));
+  ENG_CUDA(h, cudaMemcpyAsync(out_len_host, b.lens, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  ENG_CUDA(h, cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+// Exact-fp32 tiled GEMM (CUDA cores) with fused epilogues + the first subsampling conv.
+//
+// This is the "precise" arithmetic mode of the engine (b200asr_config.precision = 1) and the checker the tcgen05
+// tf32 kernels (gemm_tc.cu) are validated against on the GPU.  C[M,N] = A[M,K] . W[N,K]^T, both K-major.
+// The A operand may be gathered on the fly as the im2col view of the second subsampling conv
+// (conformer_blocks.py:81-85: 3x3, stride 2, 'same'), so conv1's activations are read in place.
+#include "kernels.cuh"
+
+namespace b200asr {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+struct ARow {
+  const float* base;  // pointer to k = 0 of this row for plain; unused for conv2
+  int b, t2, f2;
+  bool valid;
+};
+
+template <int AMODE>
+__device__ __forceinline__ float4 load_a(const GemmParams& p, int m, int k) {
+  if (m >= p.M) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (AMODE == 0) {
+    return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
+  } else {
+    const int f2 = m % p.F2;
+    const int r = m / p.F2;
+    const int t2 = r % p.T2;
+    const int b = r / p.T2;
+    const int tap = k / p.D;
+    const int c = k - tap * p.D;
+    const int kh = tap / 3, kw = tap - kh * 3;
+    const int y = 2 * t2 + kh - p.pad_t;
+    const int x = 2 * f2 + kw - p.pad_f;
+    if (y < 0 || y >= p.T1 || x < 0 || x >= p.F1) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return *reinterpret_cast<const float4*>(p.A + (((size_t)b * p.T1 + y) * p.F1 + x) * p.D + c);
+  }
+}
+
+template <int AMODE, int EPI>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  const int a_row = tid >> 2, a_kq = (tid & 3) * 4;
+  const int b_row = tid >> 2, b_kq = (tid & 3) * 4;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float4 ra0, ra1, rb;
+  auto gload = [&](int k0) {
+    ra0 = load_a<AMODE>(p, m0 + a_row, k0 + a_kq);
+    ra1 = load_a<AMODE>(p, m0 + a_row + 64, k0 + a_kq);
+    const int n = n0 + b_row;
+    rb = (n < p.N) ? *reinterpret_cast<const float4*>(p.W + (size_t)n * p.K + k0 + b_kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  gload(0);
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    As[a_kq + 0][a_row] = ra0.x; As[a_kq + 1][a_row] = ra0.y; As[a_kq + 2][a_row] = ra0.z; As[a_kq + 3][a_row] = ra0.w;
+    As[a_kq + 0][a_row + 64] = ra1.x; As[a_kq + 1][a_row + 64] = ra1.y; As[a_kq + 2][a_row + 64] = ra1.z; As[a_kq + 3][a_row + 64] = ra1.w;
+    Bs[b_kq + 0][b_row] = rb.x; Bs[b_kq + 1][b_row] = rb.y; Bs[b_kq + 2][b_row] = rb.z; Bs[b_kq + 3][b_row] = rb.w;
+    __syncthreads();
+    if (k0 + BK < p.K) gload(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int n = n0 + tx * 4;
+  if (n >= p.N) return;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (EPI != EPI_NONE && p.bias != nullptr) {
+    const float4 bq = *reinterpret_cast<const float4*>(p.bias + n);
+    bias[0] = bq.x; bias[1] = bq.y; bias[2] = bq.z; bias[3] = bq.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
+    if (EPI == EPI_GLU) {
+      float2 o;
+      o.x = v[0] * sigmoidf_(v[1]);
+      o.y = v[2] * sigmoidf_(v[3]);
+      *reinterpret_cast<float2*>(p.C + (size_t)m * p.ldc + (n >> 1)) = o;
+    } else {
+      if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (EPI == EPI_BIAS_SWISH) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = swishf_(v[j]);
+      } else if (EPI == EPI_RESID) {
+        const float4 r = *reinterpret_cast<const float4*>(p.resid + (size_t)m * p.ldc + n);
+        v[0] = r.x + p.alpha * v[0]; v[1] = r.y + p.alpha * v[1]; v[2] = r.z + p.alpha * v[2]; v[3] = r.w + p.alpha * v[3];
+      }
+      *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+template <int AMODE>
+int dispatch(const GemmParams& p, int epi, dim3 grid, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS: gemm_simt_kernel<AMODE, EPI_BIAS><<<grid, 256, 0, s>>>(p); break;
+    case EPI_BIAS_RELU: gemm_simt_kernel<AMODE, EPI_BIAS_RELU><<<grid, 256, 0, s>>>(p); break;
+    case EPI_BIAS_SWISH: gemm_simt_kernel<AMODE, EPI_BIAS_SWISH><<<grid, 256, 0, s>>>(p); break;
+    case EPI_GLU: gemm_simt_kernel<AMODE, EPI_GLU><<<grid, 256, 0, s>>>(p); break;
+    case EPI_RESID: gemm_simt_kernel<AMODE, EPI_RESID><<<grid, 256, 0, s>>>(p); break;
+    case EPI_NONE: gemm_simt_kernel<AMODE, EPI_NONE><<<grid, 256, 0, s>>>(p); break;
+    default: snprintf(g_errbuf, sizeof(g_errbuf), "gemm_simt: bad epilogue %d", epi); return 1;
+  }
+  return 0;
+}
+
+// conv1: 3x3 stride (2,2) 'same' on a single input channel + ReLU (conformer_blocks.py:76-80).
+__global__ void __launch_bounds__(256) conv1_kernel(const Conv1Params p) {
+  const size_t total = (size_t)p.B * p.T1 * p.F1 * p.D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p.D);
+    size_t r = i / p.D;
+    const int f1 = (int)(r % p.F1); r /= p.F1;
+    const int t1 = (int)(r % p.T1);
+    const int b = (int)(r / p.T1);
+    float acc = p.bias[c];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int y = 2 * t1 + kh - p.pad_t;
+      if (y < 0 || y >= p.T) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int x = 2 * f1 + kw - p.pad_f;
+        if (x < 0 || x >= p.F) continue;
+        acc = fmaf(p.mel[((size_t)b * p.T + y) * p.F + x], p.w[(kh * 3 + kw) * p.D + c], acc);
+      }
+    }
+    p.out[i] = fmaxf(acc, 0.f);
+  }
+}
+
+}  // namespace
+
+int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream) {
+  if (p.K % BK != 0 || p.N % 4 != 0 || (p.a_mode == 1 && p.D % BK != 0)) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "gemm_simt: unsupported shape M=%d N=%d K=%d", p.M, p.N, p.K);
+    return 1;
+  }
+  if (p.M == 0) return 0;
+  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN));
+  int rc = p.a_mode == 0 ? dispatch<0>(p, epilogue, grid, stream) : dispatch<1>(p, epilogue, grid, stream);
+  if (rc) return rc;
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv1(const Conv1Params& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.B * p.T1 * p.F1 * p.D;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  conv1_kernel<<<blocks, 256, 0, stream>>>(p);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200asr

@@ -1,0 +1,96 @@
+// Kernel launch interfaces (internal).  All pointers are device pointers, all launches are asynchronous on `stream`.
+#pragma once
+#include "common.cuh"
+
+namespace b200asr {
+
+// ------------------------------------------------------------------------------------------- frontend.cu
+struct FrontendParams {
+  const float* wav;        // [B, L]
+  const float* window;     // [1024]
+  const float2* twiddle;   // [1024] exp(-2*pi*i*m/1024)
+  const float* melw;       // [513, n_mels]
+  const int* mel_lo;       // [n_mels] first bin with non-zero weight
+  const int* mel_hi;       // [n_mels] one past last
+  float* power;            // [B, T, power_stride] scratch
+  unsigned int* pmax;      // [B] scratch
+  float* mel;              // [B, T, n_mels] out
+  int B, L, T, pad_left, hop, power_stride, n_mels;
+  int mode;                // 0 offline ('same', dB w/ per-utterance max), 1 chunk ('valid', log10 only)
+};
+int launch_frontend(const FrontendParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------- subsample.cu
+struct Conv1Params {
+  const float* mel;   // [B, T, F]
+  const float* w;     // [9, D] tap-major
+  const float* bias;  // [D]
+  float* out;         // [B, T1, F1, D]
+  int B, T, F, T1, F1, D, pad_t, pad_f;
+};
+int launch_conv1(const Conv1Params& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------- gemm_simt.cu
+enum Epilogue : int {
+  EPI_BIAS = 0,        // C = acc + bias
+  EPI_BIAS_RELU = 1,   // C = relu(acc + bias)
+  EPI_BIAS_SWISH = 2,  // C = swish(acc + bias)
+  EPI_GLU = 3,         // C[:, j] = (acc[2j]+b[2j]) * sigmoid(acc[2j+1]+b[2j+1])   (weights pre-interleaved), ldc = N/2
+  EPI_RESID = 4,       // C = resid + alpha * (acc + bias)
+  EPI_NONE = 5,        // C = acc
+};
+
+struct GemmParams {
+  const float* A;      // [M, K] row-major (lda), or conv2 source [B, T1, F1, D] when a_mode == 1
+  const float* W;      // [N, K] row-major (K-major "B" operand)
+  const float* bias;   // [N] or null
+  const float* resid;  // [M, ldc] (EPI_RESID)
+  float* C;            // [M, ldc]
+  int M, N, K, lda, ldc;
+  float alpha;
+  // implicit-GEMM geometry for the second subsampling conv (3x3, stride 2, TF 'same')
+  int a_mode;          // 0 plain, 1 conv2 im2col
+  int T1, F1, T2, F2, D, pad_t, pad_f;
+};
+int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------- block_ops.cu
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, float eps,
+                     cudaStream_t stream);
+
+struct AttnParams {
+  const float* qkv;   // [B*T, 3*H*dh]: q | k | v, each h-major (q already scaled by 1/sqrt(dh) through Wq)
+  float* out;         // [B*T, H*dh]
+  int B, T, H, dh;
+  // optional band mask (ChunkConformer, chunk_conformer_blocks.py:158-176); win_front < 0 => full attention
+  int win_front, win_back;
+};
+int launch_attention(const AttnParams& p, cudaStream_t stream);
+
+struct DwConvParams {
+  const float* x;   // [B*T, D]
+  const float* w;   // [K, D]
+  float* y;         // [B*T, D]
+  int B, T, D, K, pad_left;
+};
+int launch_dwconv(const DwConvParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------- ctc_decode.cu
+// argmax over V per frame (first maximum wins, as ctc_greedy_decoder.h:11-18), then merge repeats / drop blank.
+int launch_ctc_greedy(const float* logits, const int* lengths /*nullable*/, int B, int T, int V, int blank,
+                      int* frame_argmax /*[B*T] scratch*/, int* ids /*[B, T]*/, int* out_len /*[B]*/, cudaStream_t stream);
+
+struct BeamParams {
+  const float* logits;   // [B, T, V] (pre-softmax) -- softmax is applied inside, as the callers of ctc_beam_search_decoder do
+  const int* lengths;    // nullable
+  int B, T, V, blank, beam, cutoff_top_n;
+  float cutoff_prob;
+  int* ids;              // [B, beam, T]
+  int* out_len;          // [B, beam]
+  float* scores;         // [B, beam]
+  void* workspace;       // beam_workspace_bytes(B, T, beam)
+};
+size_t beam_workspace_bytes(int B, int T, int beam);
+int launch_ctc_beam(const BeamParams& p, cudaStream_t stream);
+
+}  // namespace b200asr

@@ -1,0 +1,262 @@
+"""ctypes binding of libb200asr.so (include/b200asr.h).  PyTorch only supplies device memory and streams.
+
+The product path has no CPU fallback: if the CUDA library is missing or no sm_100 GPU is present, constructing
+an Engine raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import weights as W
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200asr.so")
+
+PRECISION_TF32 = 0
+PRECISION_FP32 = 1
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32),
+                ("dmodel", ctypes.c_int32), ("num_blocks", ctypes.c_int32), ("num_heads", ctypes.c_int32),
+                ("head_size", ctypes.c_int32), ("kernel_size", ctypes.c_int32), ("ff_dim", ctypes.c_int32),
+                ("ctc_blocks", ctypes.c_int32), ("ctc_kernel_size", ctypes.c_int32), ("vocab", ctypes.c_int32),
+                ("n_mels", ctypes.c_int32), ("n_dft", ctypes.c_int32), ("hop", ctypes.c_int32),
+                ("ln_eps", ctypes.c_float),
+                ("chunk_samples", ctypes.c_int32), ("precision", ctypes.c_int32), ("use_cuda_graph", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 8)]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.b200asr_abi_version.restype = ci
+    lib.b200asr_create.restype = ci
+    lib.b200asr_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(Config), ci, ctypes.POINTER(vp)]
+    lib.b200asr_destroy.argtypes = [vp]
+    lib.b200asr_last_error.restype = ctypes.c_char_p
+    lib.b200asr_last_error.argtypes = [vp]
+    lib.b200asr_out_frames.restype = ci
+    lib.b200asr_out_frames.argtypes = [vp, ci]
+    lib.b200asr_reserve.argtypes = [vp, ci, ci]
+    lib.b200asr_encode.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.b200asr_mel.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.b200asr_ctc_logits.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.b200asr_ctc_greedy.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]
+    if hasattr(lib, "b200asr_ctc_beam"):
+        lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
+    lib.b200asr_recognize.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.b200asr_recognize_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.b200asr_launch_count.restype = ctypes.c_int64
+    lib.b200asr_launch_count.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine:
+    """One b200asr handle on one GPU."""
+
+    def __init__(self, enc_geo: W.ModelGeometry, enc_raw: Dict[str, np.ndarray],
+                 ctc_geo: Optional[W.ModelGeometry] = None, ctc_raw: Optional[Dict[str, np.ndarray]] = None,
+                 device: int = 0, precision: int = PRECISION_TF32, chunk_samples: int = 0, use_cuda_graph: bool = True):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200asr needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device = device
+        self.enc_geo, self.ctc_geo = enc_geo, ctc_geo
+        blob = W.pack_blob(W.device_tensors(enc_geo, enc_raw, ctc_geo, ctc_raw))
+        cfg = Config()
+        cfg.abi_version = self.lib.b200asr_abi_version()
+        cfg.dmodel, cfg.num_blocks, cfg.num_heads = enc_geo.dmodel, enc_geo.num_blocks, enc_geo.num_heads
+        cfg.head_size, cfg.kernel_size, cfg.ff_dim = enc_geo.head_size, enc_geo.kernel_size, enc_geo.ff_dim
+        cfg.ctc_blocks = ctc_geo.num_blocks if ctc_geo else 0
+        cfg.ctc_kernel_size = ctc_geo.kernel_size if ctc_geo else 0
+        cfg.vocab = ctc_geo.vocab if ctc_geo else 0
+        cfg.n_mels, cfg.n_dft, cfg.hop, cfg.ln_eps = enc_geo.n_mels, enc_geo.n_dft, enc_geo.hop, enc_geo.ln_eps
+        cfg.chunk_samples, cfg.precision, cfg.use_cuda_graph = int(chunk_samples), int(precision), int(bool(use_cuda_graph))
+        self.cfg = cfg
+        h = ctypes.c_void_p()
+        torch.cuda.set_device(device)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        rc = self.lib.b200asr_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(cfg), device, ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("b200asr_create: " + self.lib.b200asr_last_error(None).decode(errors="replace"))
+        self._h = h
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b200asr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what}: " + self.lib.b200asr_last_error(self._h).decode(errors="replace"))
+
+    @staticmethod
+    def _stream() -> int:
+        return int(_torch().cuda.current_stream().cuda_stream)
+
+    def _dev(self):
+        return _torch().device("cuda", self.device)
+
+    def out_frames(self, num_samples: int) -> int:
+        return int(self.lib.b200asr_out_frames(self._h, int(num_samples)))
+
+    def reserve(self, B: int, L: int):
+        self._check(self.lib.b200asr_reserve(self._h, int(B), int(L)), "b200asr_reserve")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b200asr_launch_count(self._h))
+
+    def _as_wav(self, wav):
+        torch = _torch()
+        if isinstance(wav, np.ndarray):
+            wav = torch.from_numpy(np.ascontiguousarray(wav, dtype=np.float32))
+        wav = wav.to(device=self._dev(), dtype=torch.float32)
+        if wav.dim() == 3:
+            wav = wav[..., 0]
+        if wav.dim() == 1:
+            wav = wav[None, :]
+        return wav.contiguous()
+
+    # ------------------------------------------------------------------------------------------------ ops
+    def mel(self, wav):
+        torch = _torch()
+        wav = self._as_wav(wav)
+        B, L = wav.shape
+        T = -(-L // self.enc_geo.hop)
+        out = torch.empty((B, T, self.enc_geo.n_mels), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_mel(self._h, wav.data_ptr(), B, L, out.data_ptr(), self._stream()), "b200asr_mel")
+        return out
+
+    def encode(self, wav, out=None):
+        """wav [B, L] (or [B, L, 1]) -> encoder states [B, T', D] on the GPU."""
+        torch = _torch()
+        wav = self._as_wav(wav)
+        B, L = wav.shape
+        Tp = self.out_frames(L)
+        if out is None:
+            out = torch.empty((B, Tp, self.enc_geo.dmodel), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_encode(self._h, wav.data_ptr(), B, L, out.data_ptr(), self._stream()), "b200asr_encode")
+        return out
+
+    def ctc_logits(self, enc, out=None):
+        torch = _torch()
+        if isinstance(enc, np.ndarray):
+            enc = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32))
+        enc = enc.to(device=self._dev(), dtype=torch.float32).contiguous()
+        B, Tp, _ = enc.shape
+        if out is None:
+            out = torch.empty((B, Tp, self.ctc_geo.vocab), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_ctc_logits(self._h, enc.data_ptr(), B, Tp, out.data_ptr(), self._stream()),
+                    "b200asr_ctc_logits")
+        return out
+
+    def ctc_greedy(self, logits, lengths=None, blank: Optional[int] = None):
+        """logits [B, T, V] -> (ids [B, T] int32 padded with -1, lengths [B] int32)."""
+        torch = _torch()
+        if isinstance(logits, np.ndarray):
+            logits = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32))
+        logits = logits.to(device=self._dev(), dtype=torch.float32).contiguous()
+        B, T, V = logits.shape
+        blank = V - 1 if blank is None else int(blank)
+        ids = torch.empty((B, T), device=self._dev(), dtype=torch.int32)
+        lens = torch.empty((B,), device=self._dev(), dtype=torch.int32)
+        lptr = None
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths, dtype=torch.int32).to(self._dev()).contiguous()
+            lptr = lengths.data_ptr()
+        self._check(self.lib.b200asr_ctc_greedy(self._h, logits.data_ptr(), lptr, B, T, V, blank, ids.data_ptr(),
+                                                lens.data_ptr(), self._stream()), "b200asr_ctc_greedy")
+        return ids, lens
+
+    def ctc_beam(self, logits, beam: int, lengths=None, blank: Optional[int] = None, cutoff_top_n: int = 40,
+                 cutoff_prob: float = 1.0):
+        """Prefix beam search (no scorer).  -> (ids [B, beam, T] int32 -1 padded, lens [B, beam], scores [B, beam])."""
+        torch = _torch()
+        if isinstance(logits, np.ndarray):
+            logits = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32))
+        logits = logits.to(device=self._dev(), dtype=torch.float32).contiguous()
+        B, T, V = logits.shape
+        blank = V - 1 if blank is None else int(blank)
+        ids = torch.empty((B, beam, T), device=self._dev(), dtype=torch.int32)
+        lens = torch.empty((B, beam), device=self._dev(), dtype=torch.int32)
+        scores = torch.empty((B, beam), device=self._dev(), dtype=torch.float32)
+        lptr = None
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths, dtype=torch.int32).to(self._dev()).contiguous()
+            lptr = lengths.data_ptr()
+        self._check(self.lib.b200asr_ctc_beam(self._h, logits.data_ptr(), lptr, B, T, V, blank, int(beam), int(cutoff_top_n),
+                                              float(cutoff_prob), ids.data_ptr(), lens.data_ptr(), scores.data_ptr(),
+                                              self._stream()), "b200asr_ctc_beam")
+        return ids, lens, scores
+
+    def recognize(self, wav, ids=None, lens=None):
+        """wav [B, L] on the GPU -> greedy ids [B, T'] (-1 padded) + lengths, all on the GPU (no sync)."""
+        torch = _torch()
+        wav = self._as_wav(wav)
+        B, L = wav.shape
+        Tp = self.out_frames(L)
+        if ids is None:
+            ids = torch.empty((B, Tp), device=self._dev(), dtype=torch.int32)
+        if lens is None:
+            lens = torch.empty((B,), device=self._dev(), dtype=torch.int32)
+        self._check(self.lib.b200asr_recognize(self._h, wav.data_ptr(), B, L, ids.data_ptr(), lens.data_ptr(), self._stream()),
+                    "b200asr_recognize")
+        return ids, lens
+
+    def recognize_host(self, wav_host, ids_host=None, lens_host=None):
+        """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Synchronises."""
+        torch = _torch()
+        if isinstance(wav_host, np.ndarray):
+            wav_host = torch.from_numpy(np.ascontiguousarray(wav_host, dtype=np.float32))
+        if wav_host.dim() == 3:
+            wav_host = wav_host[..., 0]
+        wav_host = wav_host.contiguous()
+        B, L = wav_host.shape
+        Tp = self.out_frames(L)
+        if ids_host is None:
+            ids_host = torch.empty((B, Tp), dtype=torch.int32).pin_memory()
+        if lens_host is None:
+            lens_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self._check(self.lib.b200asr_recognize_host(self._h, wav_host.data_ptr(), B, L, ids_host.data_ptr(),
+                                                    lens_host.data_ptr(), self._stream()), "b200asr_recognize_host")
+        return ids_host, lens_host
+
+
+def engine_from_onnx(model_dir: str, device: int = 0, precision: int = PRECISION_TF32, chunk_samples: int = 0,
+                     use_cuda_graph: bool = True) -> Engine:
+    """Build an Engine from the reference's deployment directory (encoder.onnx + ctc_model.onnx), the same files
+    Inference/PythonInference/asr/src/asr.py:22-25 loads."""
+    ge, re_ = W.import_encoder(os.path.join(model_dir, "encoder.onnx"))
+    gc, rc = W.import_ctc_model(os.path.join(model_dir, "ctc_model.onnx"))
+    return Engine(ge, re_, gc, rc, device=device, precision=precision, chunk_samples=chunk_samples,
+                  use_cuda_graph=use_cuda_graph)

@@ -520,3 +520,101 @@ def random_model(seed: int, dmodel: int = 144, num_blocks: int = 2, num_heads: i
     ctc["ctc.fc.b"] = (rng.standard_normal(vocab) * 0.5).astype(np.float32)
     geo_c = ModelGeometry(D, ctc_blocks, num_heads, head_size, kernel_size, F, vocab=vocab)
     return geo_e, enc, geo_c, ctc
+
+
+# --------------------------------------------------------------------------------------------------------
+# device packing
+# --------------------------------------------------------------------------------------------------------
+def _pack_block(raw: Dict[str, np.ndarray], src: str, dst: str, out: Dict[str, np.ndarray]):
+    """One ConformerBlock -> device layout: every GEMM operand as [N, K] (K contiguous)."""
+    for k in (1, 2):
+        s, d = f"{src}ffn{k}", f"{dst}ffn{k}"
+        out[d + ".ln.g"] = raw[s + ".ln.g"]
+        out[d + ".ln.b"] = raw[s + ".ln.b"]
+        out[d + ".w1"] = raw[s + ".w1"].T
+        out[d + ".b1"] = raw[s + ".b1"]
+        out[d + ".w2"] = raw[s + ".w2"].T
+        out[d + ".b2"] = raw[s + ".b2"]
+    s, d = f"{src}mhsa", f"{dst}mhsa"
+    wq, wk, wv, wo = raw[s + ".wq"], raw[s + ".wk"], raw[s + ".wv"], raw[s + ".wo"]
+    H, D, dh = wq.shape
+    # rows h*dh+o; 1/sqrt(dh) (multihead_attention.py:158-159) folded into Wq
+    q = wq.transpose(0, 2, 1).reshape(H * dh, D) * np.float32(1.0 / np.sqrt(np.float32(dh)))
+    k_ = wk.transpose(0, 2, 1).reshape(H * dh, D)
+    v = wv.transpose(0, 2, 1).reshape(H * dh, D)
+    out[d + ".ln.g"] = raw[s + ".ln.g"]
+    out[d + ".ln.b"] = raw[s + ".ln.b"]
+    out[d + ".wqkv"] = np.concatenate([q, k_, v], axis=0)
+    out[d + ".wo"] = wo.reshape(H * dh, D).T
+    out[d + ".bo"] = raw[s + ".bo"]
+    s, d = f"{src}conv", f"{dst}conv"
+    out[d + ".ln.g"] = raw[s + ".ln.g"]
+    out[d + ".ln.b"] = raw[s + ".ln.b"]
+    pw1 = raw[s + ".pw1.w"].T                       # [2D, D], rows: a-half then b-half
+    Dm = pw1.shape[1]
+    inter = np.empty_like(pw1)
+    inter[0::2] = pw1[:Dm]                          # GLU pairs (a_j, b_j) in adjacent output columns
+    inter[1::2] = pw1[Dm:]
+    b1 = raw[s + ".pw1.b"]
+    bi = np.empty_like(b1)
+    bi[0::2] = b1[:Dm]
+    bi[1::2] = b1[Dm:]
+    out[d + ".pw1.w"] = inter
+    out[d + ".pw1.b"] = bi
+    out[d + ".dw.w"] = raw[s + ".dw.w"]
+    scale, shift = raw[s + ".bn.scale"], raw[s + ".bn.shift"]
+    out[d + ".pw.w"] = (raw[s + ".pw.w"] * scale[None, :]).T          # eval-mode BatchNorm folded into the pointwise conv
+    out[d + ".pw.b"] = raw[s + ".pw.b"] * scale + shift
+    out[d + ".pw2.w"] = raw[s + ".pw2.w"].T
+    out[d + ".pw2.b"] = raw[s + ".pw2.b"]
+    out[f"{dst}ln.g"] = raw[f"{src}ln.g"]
+    out[f"{dst}ln.b"] = raw[f"{src}ln.b"]
+
+
+def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_geo: Optional[ModelGeometry] = None,
+                   ctc_raw: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+    out: Dict[str, np.ndarray] = {}
+    D = enc_geo.dmodel
+    out["fe.window"] = enc_raw["fe.window"]
+    out["fe.mel"] = enc_raw["fe.mel"]
+    out["sub.conv1.w"] = enc_raw["sub.conv1.w"].reshape(9, D)                                   # [(kh,kw), D]
+    out["sub.conv1.b"] = enc_raw["sub.conv1.b"]
+    out["sub.conv2.w"] = enc_raw["sub.conv2.w"].transpose(3, 0, 1, 2).reshape(D, 9 * D)         # [Cout, (kh,kw,Cin)]
+    out["sub.conv2.b"] = enc_raw["sub.conv2.b"]
+    out["sub.lin.w"] = enc_raw["sub.lin.w"].T                                                   # [D, F2*D]
+    out["sub.lin.b"] = enc_raw["sub.lin.b"]
+    for i in range(enc_geo.num_blocks):
+        _pack_block(enc_raw, f"enc.{i}.", f"enc.{i}.", out)
+    if ctc_raw is not None:
+        out["ctc.proj.w"] = ctc_raw["ctc.proj.w"].T
+        out["ctc.proj.b"] = ctc_raw["ctc.proj.b"]
+        for i in range(ctc_geo.num_blocks):
+            _pack_block(ctc_raw, f"ctc.blk{i}.", f"ctc.blk{i}.", out)
+        out["ctc.fc.w"] = ctc_raw["ctc.fc.w"].T                                                 # [V, D]
+        out["ctc.fc.b"] = ctc_raw["ctc.fc.b"]
+    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+
+
+def pack_blob(tensors: Dict[str, np.ndarray]) -> bytes:
+    """Serialise to the blob format documented in include/b200asr.h."""
+    import struct
+    names = list(tensors.keys())
+    header = 16 + 64 * len(names)
+    off = (header + 127) // 128 * 128
+    table = bytearray()
+    chunks = []
+    for n in names:
+        a = tensors[n]
+        nb = n.encode()
+        if len(nb) > 47:
+            raise ValueError(f"tensor name too long: {n}")
+        table += nb.ljust(48, b"\0") + struct.pack("<QQ", off, a.size)
+        chunks.append((off, a.tobytes()))
+        off = (off + a.nbytes + 127) // 128 * 128
+    blob = bytearray(off)
+    blob[0:8] = b"B2ASRW01"
+    blob[8:16] = struct.pack("<II", len(names), 0)
+    blob[16:16 + len(table)] = table
+    for o, data in chunks:
+        blob[o:o + len(data)] = data
+    return bytes(blob)
