@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 Conformer-CTC hot path (BASELINE.json metric: audio frames/sec, 16 kHz, 10 s utterances).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision tf32|fp32]
+
+A step = one pass of the hot path (wav -> mel -> ConformerCTC(S) encoder -> CTC decoder -> greedy ids) over one
+batch of 32 x 10 s synthetic 16 kHz utterances per GPU (BASELINE.json configs[1]).  1 frame = one 10 ms hop.
+`value` = frames/s with the waveforms resident in HBM (device-timed, CUDA events, max over ranks);
+`e2e`   = the same through the C-ABI call that takes HOST buffers (pinned H2D of the batch + D2H of ids inside the
+          timed region).
+N > 1 (torchrun): utterances shard across ranks (weak scaling, one replica per GPU); the only collective is the
+NCCL all_gather of the decoded ids + lengths, inside the timed region.
+`--impl reference` times the reference's own CPU deployment path (shipped ONNX graphs through its vendored
+onnxruntime 1.10.0, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH, SECONDS, SR, HOP = 32, 10, 16000, 160
+L = SECONDS * SR
+FRAMES_PER_UTT = L // HOP
+METRIC = "audio frames/sec (16 kHz, 10 s utts)"
+
+
+def synth_batch(seed: int, B: int = BATCH) -> np.ndarray:
+    """wav ~ N(0, 0.1^2) clipped to [-1, 1]; every 4th row is tiled speech so the decoder emits tokens."""
+    rng = np.random.default_rng(seed)
+    x = np.clip(rng.standard_normal((B, L)).astype(np.float32) * 0.1, -1.0, 1.0)
+    wav_path = os.path.join(ROOT, "tests", "golden", "BAC009S0764W0121.wav")
+    if os.path.isfile(wav_path):
+        import wave
+        w = wave.open(wav_path)
+        s = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768
+        x[::4] = np.tile(s, L // len(s) + 1)[:L]
+    return x
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------- reference arm
+def reference_arm(args, rank: int, world: int):
+    """The reference's own CPU implementation of the path (kind 'reference': oracle/_ref ONNX Runtime + shipped graphs)."""
+    if rank != 0:
+        return
+    from oracle import ort_ref, ctc_ref
+    line = {"impl": "reference", "metric": METRIC, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gpu_launches": 0}
+    if not ort_ref.available():
+        line["unavailable"] = "oracle/_ref (vendored onnxruntime + ONNX graphs) was not staged in this checkout"
+        print(json.dumps(line))
+        return
+    cores = os.cpu_count() or 1
+    ref = ort_ref.ReferenceASR("offline", threads=cores)
+    sample_b = 4                                         # bounded sample: 4 of the 32 utterances per step
+    x = synth_batch(1234)[:sample_b]
+
+    def step():
+        enc = ref.encode(x)
+        logits = ref.logits(enc)
+        return [ctc_ref.greedy_decode(l, logits.shape[-1] - 1) for l in logits]
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample_b * FRAMES_PER_UTT * args.steps / dt
+    line.update({"value": val, "ms_per_step": dt / args.steps * 1e3,
+                 "config": {"workload": f"ConformerCTC(S) offline greedy, {sample_b} x 10 s sample of the 32 x 10 s batch, "
+                                        "ONNX Runtime 1.10.0 CPU", "global_batch": sample_b, "seq_len": L},
+                 "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "reference",
+                                  "sample": f"{sample_b} x 10 s utterances per step, {args.steps} steps"},
+                 "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample():
+    """Bounded CPU baseline timed beside the GPU run (rank 0, N=1 only)."""
+    from oracle import ort_ref, ctc_ref
+    if not ort_ref.available():
+        return None
+    cores = os.cpu_count() or 1
+    ref = ort_ref.ReferenceASR("offline", threads=cores)
+    sample_b = 4
+    x = synth_batch(1234)[:sample_b]
+
+    def step():
+        logits = ref.logits(ref.encode(x))
+        return [ctc_ref.greedy_decode(l, logits.shape[-1] - 1) for l in logits]
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 40):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample_b * FRAMES_PER_UTT * n / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
+            "sample": f"{n} passes over {sample_b} x 10 s utterances (ONNX Runtime 1.10.0, {cores} threads)"}
+
+
+# ----------------------------------------------------------------------------------------------------------- own arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tensorflowasr_b200 import engine as E, weights as W
+    from oracle import ort_ref  # only to locate the staged reference weights; nothing from oracle/ is on the timed path
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    md = ort_ref.model_dir("offline")
+    if md is not None:
+        ge, re_ = W.import_encoder(os.path.join(md, "encoder.onnx"))
+        gc, rc = W.import_ctc_model(os.path.join(md, "ctc_model.onnx"))
+        weights_desc = "reference-trained ConformerCTC(S) weights (shipped ONNX)"
+    else:
+        ge, re_, gc, rc = W.random_model(0, num_blocks=13)
+        weights_desc = "random-init ConformerCTC(S) architecture"
+    prec = E.PRECISION_TF32 if args.precision == "tf32" else E.PRECISION_FP32
+    eng = E.Engine(ge, re_, gc, rc, device=local_rank, precision=prec, use_cuda_graph=True)
+    eng.reserve(BATCH, L)
+    Tp = eng.out_frames(L)
+
+    # inputs: NROT distinct batches (> L2 together) rotated so no step re-reads a cached waveform
+    NROT = 8
+    host = [torch.from_numpy(synth_batch(1234 + 97 * rank + i)).pin_memory() for i in range(NROT)]
+    dev = [h.cuda(non_blocking=True) for h in host]
+    ids = torch.empty((BATCH, Tp), device="cuda", dtype=torch.int32)
+    lens = torch.empty((BATCH,), device="cuda", dtype=torch.int32)
+    gather_ids = [torch.empty_like(ids) for _ in range(world)] if world > 1 else None
+    gather_lens = [torch.empty_like(lens) for _ in range(world)] if world > 1 else None
+    stream = torch.cuda.Stream()
+
+    def step(i):
+        eng.recognize(dev[i % NROT], ids, lens)
+        if world > 1:
+            dist.all_gather(gather_ids, ids)
+            dist.all_gather(gather_lens, lens)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = eng.launch_count - launches0
+
+        # end to end through the host-buffer C-ABI entry point
+        hid = torch.empty((BATCH, Tp), dtype=torch.int32).pin_memory()
+        hlen = torch.empty((BATCH,), dtype=torch.int32).pin_memory()
+        dev_in = torch.empty_like(dev[0])
+
+        def e2e_step(i):
+            if world == 1:
+                eng.recognize_host(host[i % NROT], hid, hlen)          # H2D + compute + D2H + sync inside the C-ABI call
+            else:
+                dev_in.copy_(host[i % NROT], non_blocking=True)
+                eng.recognize(dev_in, ids, lens)
+                dist.all_gather(gather_ids, ids)
+                dist.all_gather(gather_lens, lens)
+                hid.copy_(gather_ids[rank], non_blocking=True)
+                hlen.copy_(gather_lens[rank], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        for i in range(args.warmup):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+        # roofline of the dominant kernel, timed alone with CUDA events on this stream
+        roof = None
+        if rank == 0:
+            eng.recognize(dev[0], ids, lens)
+            torch.cuda.synchronize()
+            stage = "conv2"
+            ms_k, flops, bytes_ = eng.time_stage(stage, BATCH, L, iters=20)
+            hbm_peak, tf_peak, how = measured_peaks()
+            ach = flops / (ms_k * 1e-3) / 1e12
+            peak = tf_peak if args.precision == "tf32" else None
+            roof = {"kernel": "conv_subsampling conv2 (implicit GEMM M=%d N=144 K=1296, fused bias+ReLU)" % (BATCH * Tp * 20),
+                    "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}); the kernel computes in "
+                                   f"{'tf32 (half the bf16 tensor rate)' if args.precision == 'tf32' else 'fp32 on CUDA cores'}",
+                    "ms_per_launch": ms_k, "flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_, "traffic": None}
+            others = {}
+            for st in ("stft", "ffn_w1", "ffn_w2", "attention", "sub_linear", "ctc_fc"):
+                m, f, b = eng.time_stage(st, BATCH, L, iters=20)
+                others[st] = {"ms": round(m, 4), "tflops": round(f / (m * 1e-3) / 1e12, 2), "gbs": round(b / (m * 1e-3) / 1e9, 1)}
+            roof["other_stages"] = others
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    frames = BATCH * FRAMES_PER_UTT * world * args.steps
+    if rank == 0:
+        value = frames / (ms_total * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "rtf": (ms_total * 1e-3) / (BATCH * SECONDS * world * args.steps),
+                "config": {"workload": "ConformerCTC(S) 10M offline greedy, batch 32 x 10 s synthetic 16 kHz per GPU "
+                                       "(BASELINE.json configs[1])", "weights": weights_desc, "global_batch": BATCH * world,
+                           "seq_len": L, "parallelism": f"dp{world} (utterance shard, ids all_gather)",
+                           "l2_policy": f"{NROT} distinct input batches rotated ({NROT * BATCH * L * 4 / 1e6:.0f} MB > 126 MB L2); "
+                                        "per-step intermediates (369 MB conv1 map) exceed L2",
+                           "frame": "10 ms hop (160 samples)"},
+                "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": BATCH * L * 4,
+                        "d2h_bytes_per_step": BATCH * Tp * 4 + BATCH * 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample()
+            except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
+                line["cpu_baseline"] = {"error": str(ex)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

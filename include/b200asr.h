@@ -104,6 +104,13 @@ B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B,
 B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host,
                            int32_t* out_len_host, void* stream);
 
+/* Roofline instrumentation (bench.py): time one stage of the schedule alone, `iters` launches bracketed by CUDA events on
+ * `stream`; also returns that launch's algorithmic FLOPs and HBM bytes.  Run b200asr_recognize with the same (B, L) first. */
+enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 = 2, B200ASR_STAGE_STFT = 3,
+       B200ASR_STAGE_SUBLIN = 4, B200ASR_STAGE_ATTENTION = 5, B200ASR_STAGE_CTC_FC = 6 };
+B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, int iters, void* stream, float* ms_per_launch,
+                                   double* flops, double* bytes);
+
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
 

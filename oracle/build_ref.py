@@ -71,7 +71,7 @@ def build(verbose: bool = False) -> bool:
                         with open(p, "wb") as f:
                             f.write(data)
                 stubs = os.path.join(HERE, "ctcdec_stubs")
-                _run(["g++", "-O2", "-std=c++14", "-shared", "-fPIC", "-pthread", "-I" + stubs, "-I" + tmp,
+                _run(["g++", "-O2", "-std=c++14", "-shared", "-fPIC", "-pthread", "-I" + stubs, "-I" + tmp, "-I" + os.path.join(tmp, "ThreadPool"),
                       os.path.join(tmp, "ctc_beam_search_decoder.cpp"), os.path.join(tmp, "path_trie.cpp"),
                       os.path.join(tmp, "decoder_utils.cpp"), os.path.join(tmp, "ctc_greedy_decoder.cpp"), wrap, "-o", out])
     if verbose:

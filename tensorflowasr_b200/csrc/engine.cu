@@ -61,6 +61,8 @@ struct b200asr_engine {
   std::map<GraphKey, int64_t> graph_launches;
   int64_t launches = 0;
   std::string err;
+  void* beam_ws = nullptr;
+  size_t beam_ws_bytes = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   TcContext tc;  // tcgen05 GEMM state (tensor-map encoder entry point etc.)
@@ -526,6 +528,7 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   if (h->mel_lo) cudaFree(h->mel_lo);
   if (h->mel_hi) cudaFree(h->mel_hi);
   if (h->ws.base) cudaFree(h->ws.base);
+  if (h->beam_ws) cudaFree(h->beam_ws);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -618,6 +621,31 @@ B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, co
   return 0;
 }
 
+B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank,
+                     int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev,
+                     void* stream) {
+  if (!h) return 1;
+  if (B < 0 || Tp < 0 || V <= 0 || !ids_dev || !out_len_dev || !scores_dev || (!logits_dev && B * Tp > 0))
+    return fail(h, "b200asr_ctc_beam: bad arguments");
+  if (B == 0) return 0;
+  const size_t need = beam_workspace_bytes(B, Tp, std::max(beam, 1));
+  if (need > h->beam_ws_bytes) {
+    ENG_CUDA(h, cudaDeviceSynchronize());
+    if (h->beam_ws) ENG_CUDA(h, cudaFree(h->beam_ws));
+    h->beam_ws = nullptr;
+    h->beam_ws_bytes = 0;
+    ENG_CUDA(h, cudaMalloc(&h->beam_ws, need));
+    h->beam_ws_bytes = need;
+  }
+  BeamParams p{};
+  p.logits = logits_dev; p.lengths = lengths_dev; p.B = B; p.T = Tp; p.V = V; p.blank = blank; p.beam = beam;
+  p.cutoff_top_n = cutoff_top_n; p.cutoff_prob = cutoff_prob; p.ids = ids_dev; p.out_len = out_len_dev; p.scores = scores_dev;
+  p.workspace = h->beam_ws;
+  h->launches += 2;
+  ENG_TRY(h, launch_ctc_beam(p, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev, int32_t* out_len_dev,
                       void* stream) {
   if (!h) return 1;
@@ -668,6 +696,100 @@ B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, 
   ENG_CUDA(h, cudaMemcpyAsync(ids_host, b.ids, sizeof(int32_t) * (size_t)B * Tp, cudaMemcpyDeviceToHost, st));
   ENG_CUDA(h, cudaMemcpyAsync(out_len_host, b.lens, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   ENG_CUDA(h, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Time ONE stage of the schedule in isolation (bench.py roofline): `iters` back-to-back launches of the named kernel on
+// `stream`, bracketed by CUDA events on that stream; operands are whatever the last forward pass left in the workspace
+// (run b200asr_recognize with the same (B, L) first).  Also reports the stage's algorithmic FLOPs and HBM bytes per launch.
+B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, int iters, void* stream, float* ms_per_launch,
+                       double* flops, double* bytes) {
+  if (!h) return 1;
+  if (B <= 0 || L <= 0 || iters <= 0 || !ms_per_launch || !flops || !bytes) return fail(h, "b200asr_time_stage: bad arguments");
+  effective_batch(h, &B, &L);
+  Shapes s = shapes_for(h, B, L);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const b200asr_config& cfg = h->cfg;
+  const double D = cfg.dmodel, M = s.M;
+  Ctx c{h, st};
+  cudaEvent_t e0, e1;
+  ENG_CUDA(h, cudaEventCreate(&e0));
+  ENG_CUDA(h, cudaEventCreate(&e1));
+  int rc = 0;
+  for (int it = -1; it < iters && rc == 0; ++it) {   // it == -1: one untimed warm-up launch
+    if (it == 0) cudaEventRecord(e0, st);
+    switch (stage) {
+      case B200ASR_STAGE_CONV2: {
+        GemmParams g{};
+        g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = cfg.dmodel; g.K = 9 * cfg.dmodel;
+        g.ldc = cfg.dmodel; g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = cfg.dmodel; g.pad_t = s.pt2;
+        g.pad_f = s.pf2;
+        if (cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(g, EPI_BIAS_RELU)) rc = launch_gemm_tc(h->tc, g, EPI_BIAS_RELU, st);
+        else rc = launch_gemm_simt(g, EPI_BIAS_RELU, st);
+        *flops = 2.0 * g.M * D * 9.0 * D;
+        *bytes = 4.0 * ((double)s.B * s.T1 * h->F1 * D + 9.0 * D * D + (double)g.M * D);
+        break;
+      }
+      case B200ASR_STAGE_FFN_W1: {
+        const FFNW& f = h->enc_blocks[0].ffn1;
+        rc = gemm(c, b.xn, cfg.dmodel, f.w1, f.b1, nullptr, 0.f, b.h, cfg.ff_dim, s.M, cfg.ff_dim, cfg.dmodel, EPI_BIAS_SWISH);
+        *flops = 2.0 * M * D * cfg.ff_dim;
+        *bytes = 4.0 * (M * D + D * cfg.ff_dim + M * cfg.ff_dim);
+        break;
+      }
+      case B200ASR_STAGE_FFN_W2: {
+        const FFNW& f = h->enc_blocks[0].ffn1;
+        rc = gemm(c, b.h, cfg.ff_dim, f.w2, f.b2, b.x, 0.5f, b.x, cfg.dmodel, s.M, cfg.dmodel, cfg.ff_dim, EPI_RESID);
+        *flops = 2.0 * M * D * cfg.ff_dim;
+        *bytes = 4.0 * (M * cfg.ff_dim + D * cfg.ff_dim + 2.0 * M * D);
+        break;
+      }
+      case B200ASR_STAGE_STFT: {
+        rc = run_frontend(c, b.c2 /* any readable [B,L] floats */, s, b, b.mel);
+        *flops = 0.0;
+        *bytes = 4.0 * ((double)s.B * s.L + 2.0 * s.B * s.T * 513.0 + (double)s.B * s.T * cfg.n_mels);
+        break;
+      }
+      case B200ASR_STAGE_SUBLIN: {
+        rc = gemm(c, b.c2, h->F2 * cfg.dmodel, h->linw, h->linb, nullptr, 0.f, b.xn, cfg.dmodel, s.M, cfg.dmodel, h->F2 * cfg.dmodel,
+                  EPI_BIAS);
+        *flops = 2.0 * M * D * h->F2 * D;
+        *bytes = 4.0 * (M * h->F2 * D + D * h->F2 * D + M * D);
+        break;
+      }
+      case B200ASR_STAGE_ATTENTION: {
+        AttnParams ap{};
+        ap.qkv = b.h; ap.out = b.att; ap.B = s.B; ap.T = s.T2; ap.H = cfg.num_heads; ap.dh = cfg.head_size; ap.win_front = -1;
+        rc = launch_attention(ap, st);
+        *flops = 4.0 * s.B * cfg.num_heads * (double)s.T2 * s.T2 * cfg.head_size;
+        *bytes = 4.0 * (3.0 * M * cfg.num_heads * cfg.head_size + M * cfg.num_heads * cfg.head_size);
+        break;
+      }
+      case B200ASR_STAGE_CTC_FC: {
+        rc = gemm(c, b.x, cfg.dmodel, h->ctc_fcw, h->ctc_fcb, nullptr, 0.f, b.logits, cfg.vocab, s.M, cfg.vocab, cfg.dmodel, EPI_BIAS);
+        *flops = 2.0 * M * D * cfg.vocab;
+        *bytes = 4.0 * (M * D + D * cfg.vocab + M * cfg.vocab);
+        break;
+      }
+      default:
+        rc = 1;
+        snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_time_stage: unknown stage %d", stage);
+    }
+  }
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != 0) return fail_cuda(h);
+  if (e != cudaSuccess) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_time_stage: %s", cudaGetErrorString(e));
+    return fail_cuda(h);
+  }
+  *ms_per_launch = ms / iters;
   return 0;
 }
 

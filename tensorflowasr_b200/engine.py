@@ -61,6 +61,8 @@ def load_library() -> ctypes.CDLL:
         lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
     lib.b200asr_recognize.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.b200asr_time_stage.argtypes = [vp, ci, ci, ci, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_double)]
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib
@@ -232,6 +234,16 @@ class Engine:
         self._check(self.lib.b200asr_recognize(self._h, wav.data_ptr(), B, L, ids.data_ptr(), lens.data_ptr(), self._stream()),
                     "b200asr_recognize")
         return ids, lens
+
+    STAGES = {"conv2": 0, "ffn_w1": 1, "ffn_w2": 2, "stft": 3, "sub_linear": 4, "attention": 5, "ctc_fc": 6}
+
+    def time_stage(self, stage: str, B: int, L: int, iters: int = 20) -> Tuple[float, float, float]:
+        """(ms per launch, algorithmic FLOPs per launch, algorithmic HBM bytes per launch) of one kernel timed alone
+        with CUDA events on the current stream."""
+        ms, fl, by = ctypes.c_float(0), ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self.lib.b200asr_time_stage(self._h, self.STAGES[stage], int(B), int(L), int(iters), self._stream(),
+                                                ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by)), "b200asr_time_stage")
+        return float(ms.value), float(fl.value), float(by.value)
 
     def recognize_host(self, wav_host, ids_host=None, lens_host=None):
         """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Synchronises."""

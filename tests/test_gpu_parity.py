@@ -1,0 +1,262 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (ctypes binding in
+tensorflowasr_b200/engine.py), against the CPU oracle on the same seeded inputs and against golden vectors generated
+from the reference itself.
+
+Tolerances (stated per north_star "within a stated fp32 tolerance"):
+  * fp32 mode (CUDA-core GEMMs): |enc - oracle| <= 2e-4, |logits - oracle| <= 2e-3 (values up to ~30)
+  * tf32 mode (tcgen05 tensor cores, fp32 accumulate): |enc - oracle| <= 3e-2, |logits - oracle| <= 0.25
+  * mel (always fp32): 5e-3 dB on a [-80, 0] scale
+  * token ids (greedy, beam): bit-exact
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_IDS
+
+pytestmark = pytest.mark.gpu
+
+TOL = {1: dict(enc=2e-4, logits=2e-3), 0: dict(enc=3e-2, logits=0.25)}
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module", params=[1, 0], ids=["fp32", "tf32"])
+def eng(request, offline_weights):
+    from tensorflowasr_b200 import engine as E
+    ge, re_, gc, rc = offline_weights
+    e = E.Engine(ge, re_, gc, rc, precision=request.param, use_cuda_graph=True)
+    e.precision = request.param
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng32(offline_weights):
+    from tensorflowasr_b200 import engine as E
+    ge, re_, gc, rc = offline_weights
+    e = E.Engine(ge, re_, gc, rc, precision=1, use_cuda_graph=False)
+    yield e
+    e.close()
+
+
+def test_native_library_is_loaded(eng32):
+    """The product path is the in-tree CUDA library, not a framework fallback."""
+    maps = open("/proc/self/maps").read()
+    assert "libb200asr.so" in maps
+    assert eng32.launch_count == 0
+
+
+@pytest.mark.parametrize("L", [1, 159, 160, 1023, 1024, 16000, 67263])
+def test_mel_parity_ragged_lengths(eng32, offline_weights, ref_wav, L):
+    from oracle import conformer_ref as cr
+    _, re_, _, _ = offline_weights
+    x = ref_wav[None, 5000:5000 + L] if L < 60000 else ref_wav[None, :L]
+    got = eng32.mel(x).cpu().numpy()
+    ref = cr.melspectrogram(x, re_)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, atol=5e-3)
+
+
+def test_mel_vs_reference_golden(eng32, golden, ref_wav):
+    np.testing.assert_allclose(eng32.mel(ref_wav[None]).cpu().numpy()[0], golden["wav_mel"], atol=5e-3)
+
+
+def test_mel_silence_and_scale_invariance(eng32, ref_wav):
+    z = eng32.mel(np.zeros((1, 4000), np.float32)).cpu().numpy()
+    assert np.isfinite(z).all() and np.allclose(z, 0.0)          # all bins at the 1e-10 floor == the max -> 0 dB
+    a = eng32.mel(ref_wav[None, :20000]).cpu().numpy()
+    b = eng32.mel(0.25 * ref_wav[None, :20000]).cpu().numpy()
+    np.testing.assert_allclose(a, b, atol=2e-2)                   # per-utterance max normalisation
+
+
+def test_encoder_logits_ids_on_reference_wav(eng, offline_weights, golden, ref_wav, torch_mod):
+    from oracle import conformer_ref as cr
+    ge, re_, gc, rc = offline_weights
+    tol = TOL[eng.precision]
+    enc = eng.encode(ref_wav[None])
+    assert tuple(enc.shape) == (1, 106, 144)
+    enc_ref = cr.encoder_forward(ref_wav[None], re_, ge.num_blocks)
+    np.testing.assert_allclose(enc.cpu().numpy(), enc_ref, atol=tol["enc"])
+    np.testing.assert_allclose(enc.cpu().numpy()[0], golden["wav_enc"], atol=tol["enc"] + 2e-4)
+    logits = eng.ctc_logits(enc)
+    lg_ref = cr.ctc_forward(enc_ref, rc, gc.num_blocks)
+    np.testing.assert_allclose(logits.cpu().numpy(), lg_ref, atol=tol["logits"])
+    np.testing.assert_allclose(logits.cpu().numpy()[0][golden["wav_logit_frames"]], golden["wav_logits"], atol=tol["logits"] + 2e-3)
+    ids, lens = eng.ctc_greedy(logits)
+    assert ids[0, :int(lens[0])].tolist() == GOLDEN_IDS          # bit-identical greedy ids (north_star)
+    assert (ids[0, int(lens[0]):] == -1).all()
+    ids2, lens2 = eng.recognize(ref_wav[None])
+    assert ids2[0, :int(lens2[0])].tolist() == GOLDEN_IDS
+    hi, hl = eng.recognize_host(torch_mod.from_numpy(ref_wav[None]).pin_memory())
+    assert hi[0, :int(hl[0])].tolist() == GOLDEN_IDS
+
+
+def test_noise_batch_vs_oracle_and_golden(eng, offline_weights, golden, noise_2x2s):
+    from oracle import conformer_ref as cr
+    ge, re_, gc, rc = offline_weights
+    tol = TOL[eng.precision]
+    enc = eng.encode(noise_2x2s).cpu().numpy()
+    np.testing.assert_allclose(enc, cr.encoder_forward(noise_2x2s, re_, ge.num_blocks), atol=tol["enc"])
+    np.testing.assert_allclose(enc, golden["noise_enc"], atol=tol["enc"] + 3e-4)
+    ids, lens = eng.recognize(noise_2x2s)
+    logits = eng.ctc_logits(eng.encode(noise_2x2s)).cpu().numpy()
+    if eng.precision == 1:
+        assert (logits.argmax(-1) == golden["noise_argmax"]).all()
+
+
+@pytest.mark.parametrize("L", [640, 4000, 8000, 12345, 31999])
+def test_ragged_lengths_vs_oracle(eng, offline_weights, ref_wav, L):
+    """Odd lengths exercise every 'same' padding branch (odd mel / conv frame counts)."""
+    from oracle import conformer_ref as cr, ctc_ref
+    ge, re_, gc, rc = offline_weights
+    tol = TOL[eng.precision]
+    x = ref_wav[None, 10000:10000 + L]
+    enc_ref = cr.encoder_forward(x, re_, ge.num_blocks)
+    enc = eng.encode(x)
+    assert tuple(enc.shape) == enc_ref.shape
+    np.testing.assert_allclose(enc.cpu().numpy(), enc_ref, atol=tol["enc"])
+    lg_ref = cr.ctc_forward(enc_ref, rc, 1)
+    np.testing.assert_allclose(eng.ctc_logits(enc).cpu().numpy(), lg_ref, atol=tol["logits"])
+    ids, lens = eng.recognize(x)
+    assert ids[0, :int(lens[0])].tolist() == ctc_ref.greedy_decode(lg_ref[0], 1331)
+
+
+def test_batch_consistency_and_permutation(eng, ref_wav):
+    """Equal-length batches: every row equals the single-utterance result; permuting rows permutes ids."""
+    x = np.stack([ref_wav[:40000], ref_wav[20000:60000], ref_wav[:40000], ref_wav[27263:67263]])
+    ids, lens = eng.recognize(x)
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    for i in range(4):
+        si, sl = eng.recognize(x[i:i + 1])
+        assert sl[0].item() == lens[i] and (si[0].cpu().numpy() == ids[i]).all()
+    assert (ids[0] == ids[2]).all()
+    pi, pl = eng.recognize(x[[3, 1, 0, 2]])
+    assert (pi.cpu().numpy() == ids[[3, 1, 0, 2]]).all()
+
+
+def test_full_size_batch_properties(eng, ref_wav, torch_mod):
+    """BASELINE config 2 shape (32 x 10 s): finite outputs, tiled-speech rows decode identically to a single row, and the
+    host-buffer entry point agrees with the device-buffer one."""
+    L = 160000
+    speech = np.tile(ref_wav, 3)[:L]
+    rng = np.random.default_rng(1234)
+    x = np.clip(rng.standard_normal((32, L)).astype(np.float32) * 0.1, -1, 1)
+    x[::4] = speech
+    xs = torch_mod.from_numpy(x).cuda()
+    ids, lens = eng.recognize(xs)
+    enc = eng.encode(xs)
+    assert torch_mod.isfinite(enc).all()
+    assert tuple(enc.shape) == (32, 250, 144)
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    one_ids, one_len = eng.recognize(speech[None])
+    for r in range(0, 32, 4):
+        assert lens[r] == one_len[0].item() and (ids[r] == one_ids[0].cpu().numpy()).all()
+    assert lens[0] >= 30                                            # ~3 repetitions of a 13-token utterance
+    hi, hl = eng.recognize_host(torch_mod.from_numpy(x).pin_memory())
+    assert (hi.numpy() == ids).all() and (hl.numpy() == lens).all()
+
+
+# ------------------------------------------------------------------------------------------------- CTC decoders
+def test_greedy_kernel_vs_oracle(eng32, torch_mod):
+    from oracle import ctc_ref
+    rng = np.random.default_rng(5)
+    B, T, V = 5, 37, 23
+    logits = rng.standard_normal((B, T, V)).astype(np.float32) * 2
+    logits[1, :, V - 1] = 50.0                                      # all blank
+    logits[2] = 0.0                                                 # ties everywhere -> class 0 every frame
+    logits[3, :, 4] = 9.0                                           # one long repeat
+    lengths = np.array([37, 37, 37, 20, 0], np.int32)
+    ids, lens = eng32.ctc_greedy(logits, lengths=lengths)
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    for b in range(B):
+        ref = ctc_ref.greedy_decode(logits[b, :lengths[b]], V - 1) if lengths[b] else []
+        assert ids[b, :lens[b]].tolist() == ref
+        assert (ids[b, lens[b]:] == -1).all()
+    assert lens[1] == 0 and lens[2] == 1 and lens[4] == 0
+    ids0, lens0 = eng32.ctc_greedy(logits, blank=0)                 # blank_at_zero convention
+    assert ids0[2, :int(lens0[2])].tolist() == []
+
+
+def test_beam_kernel_vs_oracle_small(eng32):
+    from oracle import ctc_ref
+    rng = np.random.default_rng(9)
+    for (T, V, scale, beam, cp, ctn) in [(12, 9, 2.0, 4, 1.0, 40), (30, 40, 4.0, 8, 1.0, 40), (25, 50, 3.0, 8, 0.99, 20),
+                                          (40, 60, 6.0, 16, 1.0, 40), (20, 30, 1.0, 1, 1.0, 40), (18, 70, 5.0, 32, 1.0, 40)]:
+        logits = (rng.standard_normal((3, T, V)) * scale).astype(np.float32)
+        lengths = np.array([T, T - 3, max(T // 2, 1)], np.int32)
+        ids, lens, scores = eng32.ctc_beam(logits, beam, lengths=lengths, cutoff_prob=cp, cutoff_top_n=ctn)
+        ids, lens, scores = ids.cpu().numpy(), lens.cpu().numpy(), scores.cpu().numpy()
+        for b in range(3):
+            probs = ctc_ref.softmax(logits[b, :lengths[b]].astype(np.float32)).astype(np.float32)
+            ref = ctc_ref.beam_search(probs.astype(np.float64), beam, cutoff_prob=cp, cutoff_top_n=ctn)
+            n = len(ref)
+            got = [ids[b, k, :lens[b, k]].tolist() for k in range(beam) if lens[b, k] >= 0]
+            assert len(got) == n, (T, V, beam, len(got), n)
+            # identical hypotheses in identical order unless two neighbours tie to within float rounding
+            for k in range(n):
+                if got[k] != ref[k][1]:
+                    assert abs(ref[k][0] - scores[b, k]) < 1e-3 and sorted(map(tuple, got)) == sorted(tuple(r[1]) for r in ref)
+            np.testing.assert_allclose(scores[b, :n], [r[0] for r in ref], atol=2e-3)
+
+
+def test_beam_on_reference_wav(eng32, golden, ref_wav):
+    logits = eng32.ctc_logits(eng32.encode(ref_wav[None]))
+    ids, lens, scores = eng32.ctc_beam(logits, 16)
+    ids, lens, scores = ids.cpu().numpy()[0], lens.cpu().numpy()[0], scores.cpu().numpy()[0]
+    for k in range(4):
+        assert ids[k, :lens[k]].tolist() == golden["wav_beam_ids"][k].tolist()
+    np.testing.assert_allclose(scores[:4], golden["wav_beam_scores"], atol=2e-3)
+    assert (lens >= 0).all()                                         # the reference returns 16 hypotheses too
+    i1, l1, s1 = eng32.ctc_beam(logits, 1)
+    assert i1[0, 0, :int(l1[0, 0])].tolist() == GOLDEN_IDS           # beam 1 == greedy invariant
+
+
+# ------------------------------------------------------------------------------------------------- other geometries
+def test_streaming_model_chunks(streaming_weights, golden, ref_wav):
+    """StreamingConformerCTC (dmodel 256, 4 blocks, kernel 5): independent 8000-sample chunks, global CTC decoder."""
+    from tensorflowasr_b200 import engine as E
+    ge, re_, gc, rc = streaming_weights
+    for prec, tol in ((1, 1e-3), (0, 5e-2)):
+        e = E.Engine(ge, re_, gc, rc, precision=prec, chunk_samples=8000)
+        full = ref_wav[:64000].reshape(1, 64000)                     # 8 whole chunks in one call (reshape path, :574-594)
+        enc = e.encode(full).cpu().numpy()
+        assert enc.shape == (1, 104, 256)
+        np.testing.assert_allclose(enc[0], golden["stream_enc"][:104], atol=tol)
+        tail = e.encode(ref_wav[None, 64000:]).cpu().numpy()          # ragged last chunk on its own (test_asr.py:120-128)
+        np.testing.assert_allclose(tail[0], golden["stream_enc"][104:], atol=tol)
+        allenc = np.concatenate([enc, tail], axis=1)
+        ids, lens = e.ctc_greedy(e.ctc_logits(allenc))
+        assert ids[0, :int(lens[0])].tolist() == golden["stream_ids"].tolist()
+        e.close()
+
+
+@pytest.mark.parametrize("dmodel,heads,hs,ks", [(144, 4, 36, 32), (256, 4, 64, 5), (64, 2, 32, 7)])
+def test_random_weight_models(dmodel, heads, hs, ks):
+    from oracle import conformer_ref as cr
+    from tensorflowasr_b200 import engine as E, weights as W
+    ge, re_, gc, rc = W.random_model(3, dmodel=dmodel, num_blocks=2, num_heads=heads, head_size=hs, kernel_size=ks, vocab=100)
+    x = (np.random.default_rng(0).standard_normal((3, 9000)) * 0.1).astype(np.float32)
+    enc_ref = cr.encoder_forward(x, re_, 2)
+    lg_ref = cr.ctc_forward(enc_ref, rc, 1)
+    for prec, te, tl in ((1, 1e-3, 5e-3), (0, 8e-2, 0.5)):
+        e = E.Engine(ge, re_, gc, rc, precision=prec)
+        enc = e.encode(x)
+        np.testing.assert_allclose(enc.cpu().numpy(), enc_ref, atol=te)
+        np.testing.assert_allclose(e.ctc_logits(enc).cpu().numpy(), lg_ref, atol=tl)
+        e.close()
+
+
+def test_abi_argument_errors(eng32, torch_mod):
+    lib, h = eng32.lib, eng32._h
+    assert lib.b200asr_encode(h, None, 1, 100, None, None) != 0
+    assert b"bad arguments" in lib.b200asr_last_error(h)
+    x = torch_mod.zeros(4, device="cuda")
+    assert lib.b200asr_ctc_beam(h, x.data_ptr(), None, 1, 1, 4, 3, 99, 40, 1.0, x.data_ptr(), x.data_ptr(), x.data_ptr(), None) != 0
+    assert b"beam size" in lib.b200asr_last_error(h)
+    assert lib.b200asr_recognize(h, x.data_ptr(), 0, 100, x.data_ptr(), x.data_ptr(), None) == 0   # empty batch is a no-op

@@ -1,0 +1,112 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, weight blob layout,
+ONNX reader, shape arithmetic.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from tensorflowasr_b200 import engine as E, weights as W, onnx_reader
+
+
+def test_library_exports_every_declared_symbol():
+    lib = E.load_library()
+    header = open(os.path.join(ROOT, "include", "b200asr.h")).read()
+    declared = set(re.findall(r"B200ASR_API\s+[\w\s\*]+?\b(b200asr_\w+)\s*\(", header))
+    assert {"b200asr_create", "b200asr_encode", "b200asr_ctc_logits", "b200asr_ctc_greedy", "b200asr_ctc_beam",
+            "b200asr_recognize", "b200asr_recognize_host", "b200asr_destroy"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200asr.h but not exported"
+    assert lib.b200asr_abi_version() == 1
+
+
+def test_config_struct_matches_header():
+    header = open(os.path.join(ROOT, "include", "b200asr.h")).read()
+    body = header[header.index("typedef struct {"):header.index("} b200asr_config;")]
+    names = []
+    for line in body.splitlines():
+        line = line.split("/*")[0].strip()
+        m = re.match(r"(int32_t|float)\s+(.*);", line)
+        if m:
+            for n in m.group(2).split(","):
+                names.append(n.strip().split("[")[0])
+    assert names == [f[0] for f in E.Config._fields_]
+    assert ctypes.sizeof(E.Config) == 4 * (len(names) - 1) + 4 * 8
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ge, re_, gc, rc = W.random_model(0, num_blocks=1)
+    with pytest.raises(RuntimeError):
+        E.Engine(ge, re_, gc, rc)
+    # and the raw C entry point reports an error instead of silently falling back
+    lib = E.load_library()
+    blob = W.pack_blob(W.device_tensors(ge, re_, gc, rc))
+    cfg = E.Config()
+    cfg.abi_version = 1
+    h = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc_ = lib.b200asr_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc_ != 0 and not h.value
+    assert b"CUDA" in lib.b200asr_last_error(None)
+
+
+def test_blob_layout_roundtrip():
+    ge, re_, gc, rc = W.random_model(1, num_blocks=1)
+    t = W.device_tensors(ge, re_, gc, rc)
+    blob = W.pack_blob(t)
+    assert blob[:8] == b"B2ASRW01"
+    n = struct.unpack("<I", blob[8:12])[0]
+    assert n == len(t)
+    for i, (name, arr) in enumerate(t.items()):
+        ent = blob[16 + 64 * i:16 + 64 * (i + 1)]
+        assert ent[:48].rstrip(b"\0").decode() == name
+        off, numel = struct.unpack("<QQ", ent[48:])
+        assert off % 128 == 0 and numel == arr.size
+        np.testing.assert_array_equal(np.frombuffer(blob, np.float32, numel, off), arr.ravel())
+
+
+def test_device_packing_matches_reference_math():
+    """K-major packing, GLU interleave, BN fold and the 1/sqrt(dh) fold reproduce the raw-layout computation."""
+    from oracle import conformer_ref as cr
+    ge, re_, gc, rc = W.random_model(2, num_blocks=1)
+    t = W.device_tensors(ge, re_, gc, rc)
+    D = ge.dmodel
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, D))
+    p = "enc.0.conv"
+    y_ref = x @ re_[p + ".pw1.w"] + re_[p + ".pw1.b"]
+    glu_ref = y_ref[:, :D] * cr.sigmoid(y_ref[:, D:])
+    y = x @ t[p + ".pw1.w"].T + t[p + ".pw1.b"]
+    np.testing.assert_allclose(y[:, 0::2] * cr.sigmoid(y[:, 1::2]), glu_ref, atol=1e-5)
+    z_ref = (x @ re_[p + ".pw.w"] + re_[p + ".pw.b"]) * re_[p + ".bn.scale"] + re_[p + ".bn.shift"]
+    np.testing.assert_allclose(x @ t[p + ".pw.w"].T + t[p + ".pw.b"], z_ref, atol=1e-5)
+    m = "enc.0.mhsa"
+    q_ref = np.einsum("ni,hio->nho", x, re_[m + ".wq"]) / np.sqrt(ge.head_size)
+    qkv = x @ t[m + ".wqkv"].T
+    np.testing.assert_allclose(qkv[:, :D].reshape(3, ge.num_heads, ge.head_size), q_ref, atol=1e-5)
+    o = rng.standard_normal((3, ge.num_heads, ge.head_size))
+    np.testing.assert_allclose(o.reshape(3, -1) @ t[m + ".wo"].T, np.einsum("nhi,hio->no", o, re_[m + ".wo"]), atol=1e-5)
+    w2 = t["sub.conv2.w"].reshape(D, 3, 3, D)
+    np.testing.assert_array_equal(w2[5, 1, 2, :], re_["sub.conv2.w"][1, 2, :, 5])
+
+
+def test_onnx_reader_on_reference_model(offline_weights):
+    from oracle import ort_ref
+    g = onnx_reader.load_graph(os.path.join(ort_ref.model_dir("offline"), "ctc_model.onnx"))
+    assert g.inputs == ["inputs"] and g.outputs == ["Identity:0"]
+    assert g.initializers["fully_connected/Tensordot/ReadVariableOp:0"].shape == (144, 1332)
+    assert sum(n.op_type == "Softmax" for n in g.nodes) == 1
+
+
+def test_same_padding_arithmetic():
+    from oracle.conformer_ref import tf_same_pad
+    assert tf_same_pad(160000, 1024, 160) == (1000, 432, 432)
+    assert tf_same_pad(67263, 1024, 160) == (421, 480, 481)
+    assert tf_same_pad(1000, 3, 2) == (500, 0, 1) and tf_same_pad(421, 3, 2) == (211, 1, 1)
+    assert tf_same_pad(250, 32, 1) == (250, 15, 16)
