@@ -111,6 +111,12 @@ enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 =
 B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, int iters, void* stream, float* ms_per_launch,
                                    double* flops, double* bytes);
 
+/* Test hook: C[M,ldc] = epilogue(A[M,lda(K)] . W[N,K]^T) through the tcgen05 tf32 kernel (use_tensor_cores = 1) or the
+ * fp32 CUDA-core kernel (0).  epilogue: 0 bias, 1 bias+relu, 2 bias+swish, 3 GLU (pairs), 4 resid + alpha*(acc+bias), 5 none. */
+B200ASR_API int b200asr_debug_gemm(b200asr_handle h, const float* A, const float* W, const float* bias, const float* resid,
+                                   float* C, int M, int N, int K, int lda, int ldc, float alpha, int epilogue,
+                                   int use_tensor_cores, void* stream);
+
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
 

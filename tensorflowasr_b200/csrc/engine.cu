@@ -793,4 +793,21 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
   return 0;
 }
 
+// Test hook: one GEMM through either arithmetic path (tests/test_gpu_parity.py validates tcgen05 against fp32 CUDA cores).
+B200ASR_API int b200asr_debug_gemm(b200asr_handle h, const float* A, const float* W, const float* bias, const float* resid, float* C,
+                       int M, int N, int K, int lda, int ldc, float alpha, int epilogue, int use_tensor_cores, void* stream) {
+  if (!h) return 1;
+  GemmParams p{};
+  p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.alpha = alpha;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->launches++;
+  if (use_tensor_cores) {
+    if (!tc_gemm_supported(p, epilogue)) return fail(h, "b200asr_debug_gemm: shape not supported by the tcgen05 path");
+    ENG_TRY(h, launch_gemm_tc(h->tc, p, epilogue, st));
+  } else {
+    ENG_TRY(h, launch_gemm_simt(p, epilogue, st));
+  }
+  return 0;
+}
+
 }  // extern "C"

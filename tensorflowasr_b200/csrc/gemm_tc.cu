@@ -1,10 +1,471 @@
-// placeholder until the tcgen05 kernel lands: reports every shape as unsupported so the engine uses the fp32 path
+// tcgen05 tf32 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . W[N,K]^T), fp32 in HBM, tf32 tensor-core inputs,
+// fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes of 32 fp32 = one 128-byte swizzle row) into a
+//                              4-stage shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BLOCK_N, K=8 per
+//                              instruction, 4 per stage); tcgen05.commit releases smem stages / publishes accumulators;
+//                              also owns the TMEM allocation (512 columns = two accumulator buffers)
+//   warps 2..5  epilogue       tcgen05.ld 32 lanes x 16 columns at a time (thread == output row), fused bias / ReLU /
+//                              swish / GLU / residual, vectorised st.global; overlaps the next tile's MMAs through the
+//                              double-buffered accumulator
+// Ragged edges need no code: TMA zero-fills out-of-bounds rows (M, N tails) and columns (K tail: 144 = 4.5 x 32),
+// the epilogue masks stores.
+// The second subsampling conv (3x3, stride 2, 'same'; conformer_blocks.py:81-85) runs through the same kernel as an
+// implicit GEMM: its A operand is fetched by a 4-D tensor map over conv1's NHWC activations with traversal stride 2
+// along time and frequency, one (tap, 32-channel) slab per pipeline stage; 'same' padding is TMA out-of-bounds fill.
 #include "gemm_tc.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 namespace b200asr {
-int tc_init(TcContext* ctx) { ctx->ready = false; return 0; }
-bool tc_gemm_supported(const GemmParams&, int) { return false; }
-int launch_gemm_tc(TcContext&, const GemmParams&, int, cudaStream_t) {
-  snprintf(g_errbuf, sizeof(g_errbuf), "tcgen05 GEMM not built");
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;        // fp32 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;          // tf32
+constexpr int kStages = 4;
+constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kTmemCols = 512;
+constexpr unsigned kSpinLimit = 1u << 28;
+
+struct TcParams {
+  const float* bias;
+  const float* resid;
+  float* C;
+  int M, N, K, ldc;
+  float alpha;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  // conv2 implicit GEMM
+  int a_mode, T2, F2, D, bt, kc, pad_t, pad_f, tiles_per_b;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  unsigned spins = 0;
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > kSpinLimit) {  // a protocol bug must never hang the GPU: fail the launch instead
+      printf("b200asr gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T   (both K-major, tf32)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address  bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major) bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset = 1024 B  bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29) (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue
+template <int EPI>
+__device__ __forceinline__ void epilogue_store16(const TcParams& p, float* v, size_t row_off, int n) {
+  // v: 16 consecutive accumulator columns starting at output column n of the row at C + row_off
+  if (EPI != EPI_NONE && p.bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n + 4 * q < p.N) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + n + 4 * q);
+        v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      }
+    }
+  }
+  if (EPI == EPI_GLU) {
+    float* dst = p.C + row_off + (n >> 1);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (n + 8 * q < p.N) {
+        float4 o;
+        o.x = v[8 * q + 0] * sigmoidf_(v[8 * q + 1]);
+        o.y = v[8 * q + 2] * sigmoidf_(v[8 * q + 3]);
+        o.z = v[8 * q + 4] * sigmoidf_(v[8 * q + 5]);
+        o.w = v[8 * q + 6] * sigmoidf_(v[8 * q + 7]);
+        *reinterpret_cast<float4*>(dst + 4 * q) = o;
+      }
+    }
+    return;
+  }
+  float* dst = p.C + row_off + n;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (n + 4 * q < p.N) {
+      float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (EPI == EPI_BIAS_RELU) {
+        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+      } else if (EPI == EPI_BIAS_SWISH) {
+        o.x = swishf_(o.x); o.y = swishf_(o.y); o.z = swishf_(o.z); o.w = swishf_(o.w);
+      } else if (EPI == EPI_RESID) {
+        const float4 r = *reinterpret_cast<const float4*>(p.resid + row_off + n + 4 * q);
+        o.x = r.x + p.alpha * o.x; o.y = r.y + p.alpha * o.y; o.z = r.z + p.alpha * o.z; o.w = r.w + p.alpha * o.w;
+      }
+      *reinterpret_cast<float4*>(dst + 4 * q) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int EPI, int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 4;     // 16 KB
+  constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 4;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;     // multiple of 1024 (BLOCK_N multiple of 8)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t a_rows_bytes = (p.a_mode == 1) ? (uint32_t)(p.bt * p.F2 * BLOCK_K * 4) : kABytes;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+        const int n0 = nt * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], a_rows_bytes + kBBytes);
+          if (p.a_mode == 0) {
+            tma_load_2d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, mt * BLOCK_M);
+            tma_load_2d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0);
+          } else {
+            const int b = mt / p.tiles_per_b, tb = mt - b * p.tiles_per_b;
+            const int tap = kb / p.kc, j = kb - tap * p.kc;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(&map_a, &full_bar[stage], sa, j * BLOCK_K, kw - p.pad_f, 2 * tb * p.bt + kh - p.pad_t, b);
+            tma_load_2d(&map_b, &full_bar[stage], sb, tap * p.D + j * BLOCK_K, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in the 16-byte address field
+            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);                           // frees this smem stage when the MMAs retire
+          if (kb == p.num_k_blocks - 1) tcgen05_commit(&tmem_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;         // row inside the 128-row tile
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      bool row_ok;
+      size_t row_off;
+      if (p.a_mode == 0) {
+        const int m = mt * BLOCK_M + r;
+        row_ok = m < p.M;
+        row_off = (size_t)m * p.ldc;
+      } else {
+        const int b = mt / p.tiles_per_b, tb = mt - b * p.tiles_per_b;
+        const int i = r / p.F2, f2 = r - i * p.F2;
+        const int t2 = tb * p.bt + i;
+        row_ok = (i < p.bt) && (t2 < p.T2);
+        row_off = (((size_t)b * p.T2 + t2) * p.F2 + f2) * p.ldc;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane takes part even if its row is masked
+        const int n = nt * BLOCK_N + c;
+        if (row_ok && n < p.N) epilogue_store16<EPI>(p, v, row_off, n);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+using EncodeTiledFn = PFN_cuTensorMapEncodeTiled_v12000;
+
+int encode_map(TcContext& ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+               const cuuint32_t* box, const cuuint32_t* estr) {
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx.encode_tiled);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return 1;
+  }
+  return 0;
+}
+
+template <int BLOCK_N>
+constexpr size_t smem_bytes() {
+  return (size_t)kStages * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <int EPI, int BLOCK_N>
+int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<EPI, BLOCK_N>;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BLOCK_N>()));
+    configured = true;
+  }
+  const int tiles = tp.num_m_tiles * tp.num_n_tiles;
+  const int grid = tiles < ctx.num_sms ? tiles : ctx.num_sms;
+  kern<<<grid, kThreads, smem_bytes<BLOCK_N>(), stream>>>(ma, mb, tp);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int BLOCK_N>
+int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS: return launch_one<EPI_BIAS, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_BIAS_RELU: return launch_one<EPI_BIAS_RELU, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_BIAS_SWISH: return launch_one<EPI_BIAS_SWISH, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_GLU: return launch_one<EPI_GLU, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_RESID: return launch_one<EPI_RESID, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_NONE: return launch_one<EPI_NONE, BLOCK_N>(ctx, ma, mb, tp, s);
+  }
+  snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: bad epilogue %d", epi);
   return 1;
 }
+
+int pick_block_n(int N) {
+  if (N % 144 == 0) return 144;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N <= 144) return 144;
+  if (N <= 192) return 192;
+  if (N <= 256) return 256;
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  // ragged N (e.g. the 1332-class CTC head): fewest wasted columns among the instantiated widths
+  int best = 256, waste = (N + 255) / 256 * 256 - N;
+  const int cands[3] = {192, 144, 128};
+  for (int c : cands) {
+    const int w = (N + c - 1) / c * c - N;
+    if (w < waste) { waste = w; best = c; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int tc_init(TcContext* ctx) {
+  ctx->ready = false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "tc_init: cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return 1;
+  }
+  ctx->encode_tiled = fn;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  ctx->ready = true;
+  return 0;
+}
+
+bool tc_gemm_supported(const GemmParams& p, int epilogue) {
+  if (p.M <= 0 || p.N % 4 != 0 || p.K % 4 != 0) return false;
+  if (epilogue == EPI_GLU && p.N % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W) | reinterpret_cast<uintptr_t>(p.C)) & 15) return false;
+  if (p.a_mode == 0) return (p.lda % 4) == 0;
+  return p.F2 <= 64 && p.F2 >= 1 && (BLOCK_M / p.F2) >= 1 && (p.D % 4) == 0 && p.N == p.D && 2 * p.F2 <= 256;
+}
+
+int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream_t stream) {
+  if (!ctx.ready) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: tensor-map encoder not initialised");
+    return 1;
+  }
+  const int bn = pick_block_n(p.N);
+  TcParams tp{};
+  tp.bias = p.bias; tp.resid = p.resid; tp.C = p.C; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.ldc = p.ldc; tp.alpha = p.alpha;
+  tp.num_n_tiles = ceil_div(p.N, bn);
+  tp.a_mode = p.a_mode;
+  CUtensorMap ma, mb;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.K * 4};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
+    if (encode_map(ctx, &mb, p.W, 2, dims, strides, box, ones)) return 1;
+  }
+  if (p.a_mode == 0) {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 4};
+    const cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
+    if (encode_map(ctx, &ma, p.A, 2, dims, strides, box, ones)) return 1;
+    tp.num_m_tiles = ceil_div(p.M, BLOCK_M);
+    tp.num_k_blocks = ceil_div(p.K, BLOCK_K);
+  } else {
+    const int B = p.M / (p.T2 * p.F2);
+    tp.T2 = p.T2; tp.F2 = p.F2; tp.D = p.D; tp.pad_t = p.pad_t; tp.pad_f = p.pad_f;
+    tp.bt = BLOCK_M / p.F2;
+    tp.kc = ceil_div(p.D, BLOCK_K);
+    tp.tiles_per_b = ceil_div(p.T2, tp.bt);
+    tp.num_m_tiles = B * tp.tiles_per_b;
+    tp.num_k_blocks = 9 * tp.kc;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.D, (cuuint64_t)p.F1, (cuuint64_t)p.T1, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.D * 4, (cuuint64_t)p.F1 * p.D * 4, (cuuint64_t)p.T1 * p.F1 * p.D * 4};
+    const cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(2 * p.F2), (cuuint32_t)(2 * tp.bt), 1};
+    const cuuint32_t estr[4] = {1, 2, 2, 1};
+    if (encode_map(ctx, &ma, p.A, 4, dims, strides, box, estr)) return 1;
+  }
+  switch (bn) {
+    case 64: return dispatch_epi<64>(ctx, epilogue, ma, mb, tp, stream);
+    case 128: return dispatch_epi<128>(ctx, epilogue, ma, mb, tp, stream);
+    case 144: return dispatch_epi<144>(ctx, epilogue, ma, mb, tp, stream);
+    case 192: return dispatch_epi<192>(ctx, epilogue, ma, mb, tp, stream);
+    default: return dispatch_epi<256>(ctx, epilogue, ma, mb, tp, stream);
+  }
+}
+
 }  // namespace b200asr

@@ -63,6 +63,7 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_recognize_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_time_stage.argtypes = [vp, ci, ci, ci, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_double)]
+    lib.b200asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, vp]
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib
@@ -234,6 +235,19 @@ class Engine:
         self._check(self.lib.b200asr_recognize(self._h, wav.data_ptr(), B, L, ids.data_ptr(), lens.data_ptr(), self._stream()),
                     "b200asr_recognize")
         return ids, lens
+
+    def debug_gemm(self, A, Wt, bias=None, resid=None, alpha=1.0, epilogue=0, tensor_cores=True):
+        """Test hook: epilogue(A[M,K] @ Wt[N,K].T) on the GPU through one of the two GEMM kernels."""
+        torch = _torch()
+        M, K = A.shape
+        N = Wt.shape[0]
+        ldc = N // 2 if epilogue == 3 else N
+        C = torch.empty((M, ldc), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_debug_gemm(self._h, A.data_ptr(), Wt.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                                resid.data_ptr() if resid is not None else None, C.data_ptr(), M, N, K, K, ldc,
+                                                float(alpha), int(epilogue), int(bool(tensor_cores)), self._stream()),
+                    "b200asr_debug_gemm")
+        return C
 
     STAGES = {"conv2": 0, "ffn_w1": 1, "ffn_w2": 2, "stft": 3, "sub_linear": 4, "attention": 5, "ctc_fc": 6}
 
