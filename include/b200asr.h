@@ -117,6 +117,12 @@ B200ASR_API int b200asr_debug_gemm(b200asr_handle h, const float* A, const float
                                    float* C, int M, int N, int K, int lda, int ldc, float alpha, int epilogue,
                                    int use_tensor_cores, void* stream);
 
+/* Test hook for the fused LayerNorm epilogues (6: C = resid+alpha*(acc+bias), C2 = LN1(C); 7: C = LN1(resid+alpha*(acc+bias)),
+ * C2 = LN2(C) unless ln2_g is NULL; 8: C = acc+bias, C2 = LN1(C)).  tcgen05 path only; N in {64,128,144,192,256}. */
+B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const float* W, const float* bias, const float* resid,
+                                      float* C, float* C2, int M, int N, int K, float alpha, int epilogue, const float* ln1_g,
+                                      const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream);
+
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
 

@@ -33,6 +33,28 @@ for (M, N, K) in shapes:
         bad = (e_tc > 2e-2) or (e_32 > 1e-4) or torch.isnan(c_tc).any().item()
         ok &= not bad
         print(f"M={M:5d} N={N:5d} K={K:5d} epi={epi} err_tc={e_tc:.3e} err_fp32={e_32:.3e} mean_tc_signed={(c_tc.double()-r).mean().item():+.2e} {'BAD' if bad else ''}", flush=True)
+# fused LayerNorm epilogues
+def ln(x, g, b, eps=1e-3):
+    mu = x.mean(-1, keepdim=True); var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * g + b
+for (M, N, K) in [(8000, 144, 576), (300, 144, 144), (1000, 256, 1024), (129, 64, 128), (8000, 144, 2880)]:
+    A = torch.randn(M, K, device="cuda"); Wt = torch.randn(N, K, device="cuda") / K ** 0.5; bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda") * 30
+    g1, b1, g2, b2 = (torch.randn(N, device="cuda") for _ in range(4))
+    acc = A.double() @ Wt.double().T + bias.double()
+    for epi, inplace in ((6, False), (6, True), (7, False), (7, True), (8, False)):
+        r = resid.clone()
+        x = (r.double() + 0.5 * acc) if epi != 8 else acc
+        if epi == 7:
+            c_ref = ln(x, g1.double(), b1.double()); c2_ref = ln(c_ref, g2.double(), b2.double())
+        else:
+            c_ref = x; c2_ref = ln(x, g1.double(), b1.double())
+        C, C2 = eng.debug_gemm_ln(A, Wt, bias, r if epi != 8 else None, 0.5, epi, (g1, b1), (g2, b2) if epi == 7 else None, inplace=inplace)
+        torch.cuda.synchronize()
+        e1 = (C.double() - c_ref).abs().max().item(); e2 = (C2.double() - c2_ref).abs().max().item()
+        bad = e1 > 3e-2 or e2 > 3e-2 or torch.isnan(C2).any().item()
+        ok &= not bad
+        print(f"LN M={M} N={N} K={K} epi={epi} inplace={inplace} errC={e1:.3e} errC2={e2:.3e} {'BAD' if bad else ''}", flush=True)
 # timing of the big ones
 for (M, N, K) in [(8000, 576, 144), (8000, 144, 576), (8000, 1332, 144), (160000, 144, 1296)]:
     A = torch.randn(M, K, device="cuda"); Wt = torch.randn(N, K, device="cuda"); bias = torch.randn(N, device="cuda")

@@ -40,81 +40,153 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-// One warp per query row; keys/values streamed through shared memory in tiles of 32.  dh <= 64.
-constexpr int kQW = 8;  // queries (warps) per CTA
-__global__ void __launch_bounds__(kQW * 32) attention_kernel(const AttnParams p) {
-  extern __shared__ float sm[];
-  const int dh = p.dh, ldk = dh + 1;
-  float* Ks = sm;                 // [32][dh+1]
-  float* Vs = Ks + 32 * ldk;      // [32][dh+1]
-  float* Qs = Vs + 32 * ldk;      // [kQW][dh]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int qi = blockIdx.x * kQW + warp;
+// Flash-style attention on CUDA cores: CTA = (batch, head, 64 queries), 256 threads as 16 x 16; keys/values stream through
+// shared memory 64 at a time.  S = Q.K^T as 4x4 register micro-tiles (rows 4*ty.., columns tx+16*j so that every
+// shared-memory access is either a broadcast or conflict-free), online softmax with warp-shuffle row reductions across the
+// 16 lanes that share a query row, P staged in shared memory, O += P.V with CPT = ceil(dh/16) columns per thread.
+// No mask and no positional term in the reference (multihead_attention.py:151-188); an optional band restricts keys
+// for the chunk-streaming variant (chunk_conformer_blocks.py:158-176).
+constexpr int kAttQ = 64, kAttK = 64;
+template <int CPT>
+__global__ void __launch_bounds__(256) attention_kernel(const AttnParams p, int dhs) {
+  extern __shared__ __align__(16) float sm[];
+  const int dh = p.dh;
+  float* Qs = sm;                      // [64][dhs]
+  float* Ks = Qs + kAttQ * dhs;        // [64][dhs]
+  float* Vs = Ks + kAttK * dhs;        // [64][dhs]
+  float* Ps = Vs + kAttK * dhs;        // [64][68]
+  constexpr int PS = kAttK + 4;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttQ;
   const int ld = 3 * p.H * dh;
   const float* base = p.qkv + (size_t)b * p.T * ld;
-  const bool q_ok = qi < p.T;
-  if (q_ok) {
-    for (int d = lane; d < dh; d += 32) Qs[warp * dh + d] = base[(size_t)qi * ld + h * dh + d];
+  const int nvec = dh >> 2;            // dh % 4 == 0
+  for (int i = tid; i < kAttQ * nvec; i += 256) {
+    const int r = i / nvec, v4 = i - r * nvec;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < p.T) v = *reinterpret_cast<const float4*>(base + (size_t)(q0 + r) * ld + h * dh + 4 * v4);
+    *reinterpret_cast<float4*>(Qs + r * dhs + 4 * v4) = v;
   }
-  int lo = 0, hi = p.T - 1;
-  if (p.win_front >= 0) {  // chunk_conformer_blocks.py:158-176
-    lo = min(max(qi - p.win_front, 0), p.T - p.win_back);
-    hi = max(min(qi + p.win_back, p.T), p.win_back);
-    lo = max(lo, 0);
-    hi = min(hi, p.T - 1);
+  float m[4], l[4], o[4][CPT];
+  int lo[4], hi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) o[i][c] = 0.f;
+    const int qi = q0 + 4 * ty + i;
+    lo[i] = 0;
+    hi[i] = p.T - 1;
+    if (p.win_front >= 0) {
+      lo[i] = max(min(max(qi - p.win_front, 0), p.T - p.win_back), 0);
+      hi[i] = min(max(min(qi + p.win_back, p.T), p.win_back), p.T - 1);
+    }
   }
-  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
   const float* kbase = base + p.H * dh + h * dh;
   const float* vbase = base + 2 * p.H * dh + h * dh;
-  for (int j0 = 0; j0 < p.T; j0 += 32) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * dh; i += kQW * 32) {
-      const int j = i / dh, d = i - j * dh;
-      const int key = j0 + j;
-      float kv = 0.f, vv = 0.f;
-      if (key < p.T) {
-        kv = kbase[(size_t)key * ld + d];
-        vv = vbase[(size_t)key * ld + d];
+  for (int j0 = 0; j0 < p.T; j0 += kAttK) {
+    __syncthreads();   // previous tile fully consumed (also orders the Q staging before first use)
+    for (int i = tid; i < kAttK * nvec; i += 256) {
+      const int r = i / nvec, v4 = i - r * nvec;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j0 + r < p.T) {
+        kv = *reinterpret_cast<const float4*>(kbase + (size_t)(j0 + r) * ld + 4 * v4);
+        vv = *reinterpret_cast<const float4*>(vbase + (size_t)(j0 + r) * ld + 4 * v4);
       }
-      Ks[j * ldk + d] = kv;
-      Vs[j * ldk + d] = vv;
+      *reinterpret_cast<float4*>(Ks + r * dhs + 4 * v4) = kv;
+      *reinterpret_cast<float4*>(Vs + r * dhs + 4 * v4) = vv;
     }
     __syncthreads();
-    if (!q_ok) continue;
-    const int key = j0 + lane;
-    float s = -INFINITY;
-    if (key < p.T && key >= lo && key <= hi) {
-      s = 0.f;
-      const float* kr = Ks + lane * ldk;
-      const float* qr = Qs + warp * dh;
-      for (int d = 0; d < dh; ++d) s = fmaf(qr[d], kr[d], s);
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    for (int d = 0; d < dh; d += 4) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(Qs + (4 * ty + i) * dhs + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * dhs + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] = fmaf(qv[i].x, kv[j].x, s[i][j]);
+          s[i][j] = fmaf(qv[i].y, kv[j].y, s[i][j]);
+          s[i][j] = fmaf(qv[i].z, kv[j].z, s[i][j]);
+          s[i][j] = fmaf(qv[i].w, kv[j].w, s[i][j]);
+        }
     }
-    const float mt = warp_max(s);
-    if (mt == -INFINITY) continue;
-    const float mn = fmaxf(m, mt);
-    const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
-    const float pj = (s == -INFINITY) ? 0.f : expf(s - mn);
-    l = l * corr + warp_sum(pj);
-    acc0 *= corr;
-    acc1 *= corr;
-    m = mn;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const float pb = __shfl_sync(0xffffffffu, pj, j);
-      const float* vr = Vs + j * ldk;
-      if (lane < dh) acc0 = fmaf(pb, vr[lane], acc0);
-      if (lane + 32 < dh) acc1 = fmaf(pb, vr[lane + 32], acc1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = j0 + tx + 16 * j;
+        if (key >= p.T || key < lo[i] || key > hi[i]) s[i][j] = -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float mn = fmaxf(m[i], mx);
+      float corr = 1.f, ps = 0.f;
+      float pv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mn != -INFINITY) {
+        corr = (m[i] == -INFINITY) ? 0.f : expf(m[i] - mn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pv[j] = (s[i][j] == -INFINITY) ? 0.f : expf(s[i][j] - mn);
+          ps += pv[j];
+        }
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      l[i] = l[i] * corr + ps;
+      m[i] = mn;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) o[i][c] *= corr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ps[(4 * ty + i) * PS + tx + 16 * j] = pv[j];
+    }
+    __syncthreads();
+    for (int k = 0; k < kAttK; k += 4) {
+      float4 pr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pr[i] = *reinterpret_cast<const float4*>(Ps + (4 * ty + i) * PS + k);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const int col = tx + 16 * c;
+        if (col < dh) {
+          const float v0 = Vs[(k + 0) * dhs + col], v1 = Vs[(k + 1) * dhs + col], v2 = Vs[(k + 2) * dhs + col],
+                      v3 = Vs[(k + 3) * dhs + col];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o[i][c] = fmaf(pr[i].x, v0, o[i][c]);
+            o[i][c] = fmaf(pr[i].y, v1, o[i][c]);
+            o[i][c] = fmaf(pr[i].z, v2, o[i][c]);
+            o[i][c] = fmaf(pr[i].w, v3, o[i][c]);
+          }
+        }
+      }
     }
   }
-  if (q_ok) {
-    float* o = p.out + ((size_t)b * p.T + qi) * (p.H * dh) + h * dh;
-    const float inv = 1.0f / l;
-    if (lane < dh) o[lane] = acc0 * inv;
-    if (lane + 32 < dh) o[lane + 32] = acc1 * inv;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + 4 * ty + i;
+    if (qi >= p.T) continue;
+    const float inv = 1.0f / l[i];
+    float* orow = p.out + ((size_t)b * p.T + qi) * (p.H * dh) + h * dh;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int col = tx + 16 * c;
+      if (col < dh) orow[col] = o[i][c] * inv;
+    }
   }
 }
 
+// generic fallback (any kernel size)
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwConvParams p) {
   const size_t total = (size_t)p.B * p.T * p.D;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -129,6 +201,34 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwConvParams p) {
       if (tt >= 0 && tt < p.T) acc = fmaf(xb[(size_t)tt * p.D], p.w[j * p.D + c], acc);
     }
     p.y[i] = acc;
+  }
+}
+
+// thread = channel, TT consecutive output frames per thread: the TT+K-1 inputs and the K taps live in registers, every
+// global access is a coalesced row of D floats.  grid (ceil(T/TT), B), block = D rounded up to a warp multiple.
+template <int K, int TT>
+__global__ void __launch_bounds__(512) dwconv_reg_kernel(const DwConvParams p) {
+  const int c = threadIdx.x;
+  if (c >= p.D) return;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TT;
+  const float* xb = p.x + (size_t)b * p.T * p.D + c;
+  float w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = p.w[j * p.D + c];
+  float in[TT + K - 1];
+#pragma unroll
+  for (int i = 0; i < TT + K - 1; ++i) {
+    const int tt = t0 + i - p.pad_left;
+    in[i] = (tt >= 0 && tt < p.T) ? xb[(size_t)tt * p.D] : 0.f;
+  }
+  float* yb = p.y + (size_t)b * p.T * p.D + c;
+#pragma unroll
+  for (int o = 0; o < TT; ++o) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fmaf(in[o + j], w[j], acc);
+    if (t0 + o < p.T) yb[(size_t)(t0 + o) * p.D] = acc;
   }
 }
 
@@ -147,14 +247,31 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
 }
 
 int launch_attention(const AttnParams& p, cudaStream_t stream) {
-  if (p.dh > 64) {
-    snprintf(g_errbuf, sizeof(g_errbuf), "attention: head_size=%d > 64 unsupported", p.dh);
+  if (p.dh > 64 || p.dh % 4 != 0) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "attention: head_size=%d unsupported (needs <= 64, multiple of 4)", p.dh);
     return 1;
   }
   if (p.B == 0 || p.T == 0) return 0;
-  const size_t smem = sizeof(float) * (2 * 32 * (p.dh + 1) + kQW * p.dh);
-  dim3 grid(ceil_div(p.T, kQW), p.H, p.B);
-  attention_kernel<<<grid, kQW * 32, smem, stream>>>(p);
+  int dhs = p.dh;                       // row stride = 4 (mod 32) floats: 16-lane float4 reads hit every bank once
+  while (dhs % 32 != 4) dhs += 4;
+  const size_t smem = sizeof(float) * (size_t)(3 * 64 * dhs + 64 * 68);
+  dim3 grid(ceil_div(p.T, kAttQ), p.H, p.B);
+  const int cpt = ceil_div(p.dh, 16);
+  static bool configured = false;
+  if (!configured) {
+    const int big = (int)(sizeof(float) * (3 * 64 * 68 + 64 * 68));
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    configured = true;
+  }
+  switch (cpt) {
+    case 1: attention_kernel<1><<<grid, 256, smem, stream>>>(p, dhs); break;
+    case 2: attention_kernel<2><<<grid, 256, smem, stream>>>(p, dhs); break;
+    case 3: attention_kernel<3><<<grid, 256, smem, stream>>>(p, dhs); break;
+    default: attention_kernel<4><<<grid, 256, smem, stream>>>(p, dhs); break;
+  }
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -162,9 +279,18 @@ int launch_attention(const AttnParams& p, cudaStream_t stream) {
 int launch_dwconv(const DwConvParams& p, cudaStream_t stream) {
   const size_t total = (size_t)p.B * p.T * p.D;
   if (total == 0) return 0;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  dwconv_kernel<<<blocks, 256, 0, stream>>>(p);
+  const int threads = ceil_div(p.D, 32) * 32;
+  if (p.K == 32 && threads <= 512) {
+    constexpr int TT = 8;
+    dwconv_reg_kernel<32, TT><<<dim3(ceil_div(p.T, TT), p.B), threads, 0, stream>>>(p);
+  } else if (p.K == 5 && threads <= 512) {
+    constexpr int TT = 16;
+    dwconv_reg_kernel<5, TT><<<dim3(ceil_div(p.T, TT), p.B), threads, 0, stream>>>(p);
+  } else {
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    dwconv_kernel<<<blocks, 256, 0, stream>>>(p);
+  }
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

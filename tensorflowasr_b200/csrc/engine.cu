@@ -235,6 +235,61 @@ int gemm(Ctx& c, const float* A, int lda, const float* W, const float* bias, con
   return launch_gemm_simt(p, epi, c.s);
 }
 
+int gemm_p(Ctx& c, const GemmParams& p, int epi) {
+  c.h->launches++;
+  if (c.h->cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(p, epi)) return launch_gemm_tc(c.h->tc, p, epi, c.s);
+  if (epi >= EPI_RESID_LN) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "internal: fused-LayerNorm epilogue requested on an unsupported shape");
+    return 1;
+  }
+  return launch_gemm_simt(p, epi, c.s);
+}
+
+// Can every residual GEMM of this model carry its LayerNorm(s) in the tcgen05 epilogue?
+bool fused_ln_ok(b200asr_handle h) {
+  const int D = h->cfg.dmodel;
+  return h->cfg.precision == B200ASR_PRECISION_TF32 && h->tc.ready && (D == 64 || D == 128 || D == 144 || D == 192 || D == 256);
+}
+
+// x = resid(x) + alpha * (A.W^T + bias);  then LayerNorm(s) fused in the epilogue:
+//   ln2 == null:  C = x, C2 = LN(x; ln1)                       (EPI_RESID_LN)
+//   ln2 != null:  C = LN(x; ln1), C2 = LN(C; ln2) (if ln2->g)   (EPI_RESID_LN2)
+int gemm_resid_ln(Ctx& c, const float* A, int K, const float* W, const float* bias, float alpha, const Buffers& b, int M, int D,
+                  const LNW& ln1, const LNW* ln2, float eps) {
+  GemmParams p{};
+  p.A = A; p.W = W; p.bias = bias; p.resid = b.x; p.C = b.x; p.C2 = b.xn; p.M = M; p.N = D; p.K = K; p.lda = K; p.ldc = D;
+  p.alpha = alpha; p.ln1_g = ln1.g; p.ln1_b = ln1.b; p.ln_eps = eps;
+  if (ln2) { p.ln2_g = ln2->g; p.ln2_b = ln2->b; }
+  return gemm_p(c, p, ln2 ? EPI_RESID_LN2 : EPI_RESID_LN);
+}
+
+// One ConformerBlock with every LayerNorm folded into the epilogue of the GEMM that produces its input (11 launches).
+// Pre-condition: b.xn == LN(b.x; w.ffn1.ln).  Post-condition: b.x = block output, b.xn = LN(b.x; *next_ln) if next_ln.
+int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, int F, int H, int dh, float eps,
+                    const LNW* next_ln) {
+  const int M = B * T, HD = H * dh;
+  if (gemm(c, b.xn, D, w.ffn1.w1, w.ffn1.b1, nullptr, 0.f, b.h, F, M, F, D, EPI_BIAS_SWISH)) return 1;
+  if (gemm_resid_ln(c, b.h, F, w.ffn1.w2, w.ffn1.b2, 0.5f, b, M, D, w.mhsa.ln, nullptr, eps)) return 1;
+  if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
+  AttnParams ap{};
+  ap.qkv = b.h; ap.out = b.att; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = -1; ap.win_back = 0;
+  c.h->launches++;
+  if (launch_attention(ap, c.s)) return 1;
+  if (gemm_resid_ln(c, b.att, HD, w.mhsa.wo, w.mhsa.bo, 1.0f, b, M, D, w.conv.ln, nullptr, eps)) return 1;
+  if (gemm(c, b.xn, D, w.conv.pw1w, w.conv.pw1b, nullptr, 0.f, b.g, D, M, 2 * D, D, EPI_GLU)) return 1;
+  DwConvParams dp{};
+  dp.x = b.g; dp.w = w.conv.dww; dp.y = b.att; dp.B = B; dp.T = T; dp.D = D; dp.K = w.kernel_size;
+  dp.pad_left = same_pad(T, w.kernel_size, 1).before;
+  c.h->launches++;
+  if (launch_dwconv(dp, c.s)) return 1;
+  if (gemm(c, b.att, D, w.conv.pww, w.conv.pwb, nullptr, 0.f, b.h, 2 * D, M, 2 * D, D, EPI_BIAS_SWISH)) return 1;
+  if (gemm_resid_ln(c, b.h, 2 * D, w.conv.pw2w, w.conv.pw2b, 1.0f, b, M, D, w.ffn2.ln, nullptr, eps)) return 1;
+  if (gemm(c, b.xn, D, w.ffn2.w1, w.ffn2.b1, nullptr, 0.f, b.h, F, M, F, D, EPI_BIAS_SWISH)) return 1;
+  LNW none{nullptr, nullptr};
+  if (gemm_resid_ln(c, b.h, F, w.ffn2.w2, w.ffn2.b2, 0.5f, b, M, D, w.ln, next_ln ? next_ln : &none, eps)) return 1;
+  return 0;
+}
+
 int run_block(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, int F, int H, int dh, float eps) {
   const int M = B * T;
   const FFNW* ff[2] = {&w.ffn1, &w.ffn2};
@@ -303,6 +358,17 @@ int run_encoder(Ctx& c, const float* wav, const Shapes& s, const Buffers& b) {
   } else {
     if (launch_gemm_simt(g, EPI_BIAS_RELU, c.s)) return 1;
   }
+  if (fused_ln_ok(h) && !h->enc_blocks.empty()) {
+    GemmParams lp{};
+    lp.A = b.c2; lp.W = h->linw; lp.bias = h->linb; lp.C = b.x; lp.C2 = b.xn; lp.M = s.M; lp.N = D; lp.K = h->F2 * D;
+    lp.lda = h->F2 * D; lp.ldc = D; lp.ln1_g = h->enc_blocks[0].ffn1.ln.g; lp.ln1_b = h->enc_blocks[0].ffn1.ln.b; lp.ln_eps = cfg.ln_eps;
+    if (gemm_p(c, lp, EPI_BIAS_LN)) return 1;
+    for (size_t i = 0; i < h->enc_blocks.size(); ++i) {
+      const LNW* next = (i + 1 < h->enc_blocks.size()) ? &h->enc_blocks[i + 1].ffn1.ln : nullptr;
+      if (run_block_fused(c, h->enc_blocks[i], b, s.B, s.T2, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps, next)) return 1;
+    }
+    return 0;
+  }
   if (gemm(c, b.c2, h->F2 * D, h->linw, h->linb, nullptr, 0.f, b.x, D, s.M, D, h->F2 * D, EPI_BIAS)) return 1;
   for (const BlockW& w : h->enc_blocks)
     if (run_block(c, w, b, s.B, s.T2, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps)) return 1;
@@ -314,6 +380,20 @@ int run_ctc(Ctx& c, const float* enc, int B, int Tp, const Buffers& b, float* lo
   b200asr_handle h = c.h;
   const b200asr_config& cfg = h->cfg;
   const int D = cfg.dmodel, M = B * Tp;
+  if (fused_ln_ok(h) && !h->ctc_blocks.empty()) {
+    // projection -> (x', LN(x'; blk0.ffn1.ln)); x' must not alias the input, so the stream moves to b.g when enc == b.x
+    Buffers bb = b;
+    if (enc == b.x) std::swap(bb.x, bb.g);
+    GemmParams pp{};
+    pp.A = enc; pp.W = h->ctc_projw; pp.bias = h->ctc_projb; pp.C = bb.x; pp.C2 = bb.xn; pp.M = M; pp.N = D; pp.K = D; pp.lda = D;
+    pp.ldc = D; pp.ln1_g = h->ctc_blocks[0].ffn1.ln.g; pp.ln1_b = h->ctc_blocks[0].ffn1.ln.b; pp.ln_eps = cfg.ln_eps;
+    if (gemm_p(c, pp, EPI_BIAS_LN)) return 1;
+    for (size_t i = 0; i < h->ctc_blocks.size(); ++i) {
+      const LNW* next = (i + 1 < h->ctc_blocks.size()) ? &h->ctc_blocks[i + 1].ffn1.ln : nullptr;
+      if (run_block_fused(c, h->ctc_blocks[i], bb, B, Tp, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps, next)) return 1;
+    }
+    return gemm(c, bb.x, D, h->ctc_fcw, h->ctc_fcb, nullptr, 0.f, logits, cfg.vocab, M, cfg.vocab, D, EPI_BIAS);
+  }
   // the block schedule runs in place on its `x` buffer; when the input *is* b.x, project into b.xn and swap roles
   Buffers bb = b;
   if (enc == b.x) std::swap(bb.x, bb.xn);
@@ -807,6 +887,20 @@ B200ASR_API int b200asr_debug_gemm(b200asr_handle h, const float* A, const float
   } else {
     ENG_TRY(h, launch_gemm_simt(p, epilogue, st));
   }
+  return 0;
+}
+
+// Test hook for the fused-LayerNorm epilogues of the tcgen05 kernel (epilogue 6, 7 or 8; C may alias resid).
+B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const float* W, const float* bias, const float* resid, float* C,
+                          float* C2, int M, int N, int K, float alpha, int epilogue, const float* ln1_g, const float* ln1_b,
+                          const float* ln2_g, const float* ln2_b, float eps, void* stream) {
+  if (!h) return 1;
+  GemmParams p{};
+  p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C; p.C2 = C2; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N;
+  p.alpha = alpha; p.ln1_g = ln1_g; p.ln1_b = ln1_b; p.ln2_g = ln2_g; p.ln2_b = ln2_b; p.ln_eps = eps;
+  if (!tc_gemm_supported(p, epilogue)) return fail(h, "b200asr_debug_gemm_ln: shape not supported by the tcgen05 path");
+  h->launches++;
+  ENG_TRY(h, launch_gemm_tc(h->tc, p, epilogue, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -133,28 +133,51 @@ int dispatch(const GemmParams& p, int epi, dim3 grid, cudaStream_t s) {
   return 0;
 }
 
-// conv1: 3x3 stride (2,2) 'same' on a single input channel + ReLU (conformer_blocks.py:76-80).
-__global__ void __launch_bounds__(256) conv1_kernel(const Conv1Params p) {
-  const size_t total = (size_t)p.B * p.T1 * p.F1 * p.D;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % p.D);
-    size_t r = i / p.D;
-    const int f1 = (int)(r % p.F1); r /= p.F1;
-    const int t1 = (int)(r % p.T1);
-    const int b = (int)(r / p.T1);
-    float acc = p.bias[c];
+// conv1: 3x3 stride (2,2) 'same' on a single input channel + ReLU (conformer_blocks.py:76-80).  HBM-write bound
+// (B*T1*F1*D floats out, tiny input): one CTA per (b, group of ROWS output time rows); a thread owns 4 consecutive output
+// channels (its 9x4 weights live in registers for the whole CTA) and walks over frequency; the three mel rows an output
+// row needs are staged in shared memory; stores are 16-byte, coalesced along channels.
+constexpr int kConv1Rows = 4;
+__global__ void __launch_bounds__(256) conv1_kernel(const Conv1Params p, int groups, int flanes) {
+  extern __shared__ float mel_s[];  // [2*ROWS+1][F + 2] with one zero column of padding on each side
+  const int b = blockIdx.y;
+  const int t1_0 = blockIdx.x * kConv1Rows;
+  const int FW = p.F + 2;
+  const int nrows = 2 * kConv1Rows + 1;
+  for (int i = threadIdx.x; i < nrows * FW; i += blockDim.x) {
+    const int r = i / FW, xx = i - r * FW;
+    const int y = 2 * t1_0 + r - p.pad_t;
+    const int x = xx - 1;
+    float v = 0.f;
+    if (y >= 0 && y < p.T && x >= 0 && x < p.F) v = p.mel[((size_t)b * p.T + y) * p.F + x];
+    mel_s[i] = v;
+  }
+  const int g = threadIdx.x % groups, fl = threadIdx.x / groups;
+  float4 w[9];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int y = 2 * t1 + kh - p.pad_t;
-      if (y < 0 || y >= p.T) continue;
+  for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(p.w + k * p.D + 4 * g);
+  const float4 bias = *reinterpret_cast<const float4*>(p.bias + 4 * g);
+  __syncthreads();
+  if (fl >= flanes) return;
+  for (int r = 0; r < kConv1Rows; ++r) {
+    const int t1 = t1_0 + r;
+    if (t1 >= p.T1) break;
+    float* orow = p.out + (((size_t)b * p.T1 + t1) * p.F1) * p.D + 4 * g;
+    for (int f1 = fl; f1 < p.F1; f1 += flanes) {
+      float4 acc = bias;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int x = 2 * f1 + kw - p.pad_f;
-        if (x < 0 || x >= p.F) continue;
-        acc = fmaf(p.mel[((size_t)b * p.T + y) * p.F + x], p.w[(kh * 3 + kw) * p.D + c], acc);
+      for (int kh = 0; kh < 3; ++kh) {
+        const float* mrow = mel_s + (2 * r + kh) * FW + (2 * f1 - p.pad_f + 1);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float m = mrow[kw];
+          const float4 ww = w[kh * 3 + kw];
+          acc.x = fmaf(m, ww.x, acc.x); acc.y = fmaf(m, ww.y, acc.y); acc.z = fmaf(m, ww.z, acc.z); acc.w = fmaf(m, ww.w, acc.w);
+        }
       }
+      acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      *reinterpret_cast<float4*>(orow + (size_t)f1 * p.D) = acc;
     }
-    p.out[i] = fmaxf(acc, 0.f);
   }
 }
 
@@ -174,11 +197,17 @@ int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream) {
 }
 
 int launch_conv1(const Conv1Params& p, cudaStream_t stream) {
-  const size_t total = (size_t)p.B * p.T1 * p.F1 * p.D;
-  if (total == 0) return 0;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  conv1_kernel<<<blocks, 256, 0, stream>>>(p);
+  if ((size_t)p.B * p.T1 * p.F1 * p.D == 0) return 0;
+  if (p.D % 4 != 0 || p.D / 4 > 256 || p.pad_f > 1) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "conv1: unsupported geometry D=%d pad_f=%d", p.D, p.pad_f);
+    return 1;
+  }
+  const int groups = p.D / 4;
+  const int flanes = 256 / groups;
+  const int threads = groups * flanes;
+  const size_t smem = sizeof(float) * (2 * kConv1Rows + 1) * (p.F + 2);
+  dim3 grid(ceil_div(p.T1, kConv1Rows), p.B);
+  conv1_kernel<<<grid, threads, smem, stream>>>(p, groups, flanes);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -38,6 +38,9 @@ struct TcParams {
   float* C;
   int M, N, K, ldc;
   float alpha;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float* C2;
+  float ln_eps;
   int num_m_tiles, num_n_tiles, num_k_blocks;
   // conv2 implicit GEMM
   int a_mode, T2, F2, D, bt, kc, pad_t, pad_f, tiles_per_b;
@@ -175,6 +178,114 @@ __device__ __forceinline__ void epilogue_store16(const TcParams& p, float* v, si
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused LayerNorm epilogues
+// thread == output row and BLOCK_N == N, so a row's statistics never leave the thread: the accumulator row is swept from
+// TMEM two (three) times -- statistics (shifted one-pass variance), then normalise -- instead of being parked in registers.
+template <int EPI, int BLOCK_N>
+__device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, bool row_ok, size_t row_off) {
+  const bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
+  auto load_x = [&](int c, float* v) {
+    tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective
+    if (!row_ok) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + c + 4 * q);
+      v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      if (has_resid) {
+        const float4 r = *reinterpret_cast<const float4*>(p.resid + row_off + c + 4 * q);
+        v[4 * q + 0] = r.x + p.alpha * v[4 * q + 0]; v[4 * q + 1] = r.y + p.alpha * v[4 * q + 1];
+        v[4 * q + 2] = r.z + p.alpha * v[4 * q + 2]; v[4 * q + 3] = r.w + p.alpha * v[4 * q + 3];
+      }
+    }
+  };
+  // re-read this thread's own row from C (written earlier by this same thread): needed because C may alias resid
+  auto load_c = [&](int c, float* v) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 r = *reinterpret_cast<const float4*>(p.C + row_off + c + 4 * q);
+      v[4 * q + 0] = r.x; v[4 * q + 1] = r.y; v[4 * q + 2] = r.z; v[4 * q + 3] = r.w;
+    }
+  };
+  auto store16 = [&](float* dst, const float* v) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  };
+  auto affine16 = [&](float* v, float mean, float rstd, const float* g, const float* be, int c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 gg = *reinterpret_cast<const float4*>(g + c + 4 * q);
+      const float4 bb = *reinterpret_cast<const float4*>(be + c + 4 * q);
+      v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
+      v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
+    }
+  };
+  const float invn = 1.0f / (float)BLOCK_N;
+  // sweep 1: x (stored for *_LN modes where C holds the un-normalised stream) + statistics
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 16) {
+    float v[16];
+    load_x(c, v);
+    if (c == 0) shift = v[0];
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float d = v[i] - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+      if (EPI != EPI_RESID_LN2) store16(p.C + row_off + c, v);
+    }
+  }
+  const float m1 = s1 * invn;
+  const float mean1 = shift + m1;
+  const float rstd1 = 1.0f / sqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
+  if (EPI != EPI_RESID_LN2) {
+    // sweep 2: LN(x; ln1) -> C2   (x read back from C: the residual operand may have been overwritten in place)
+    if (!row_ok) return;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      float v[16];
+      load_c(c, v);
+      {
+        affine16(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
+        store16(p.C2 + row_off + c, v);
+      }
+    }
+    return;
+  }
+  // EPI_RESID_LN2: sweep 2: y = LN(x; ln1) -> C, statistics of y; sweep 3: LN(y; ln2) -> C2
+  float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 16) {
+    float v[16];
+    load_x(c, v);
+    if (row_ok) {
+      affine16(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
+      if (c == 0) shift2 = v[0];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float d = v[i] - shift2;
+        t1 += d;
+        t2 = fmaf(d, d, t2);
+      }
+      store16(p.C + row_off + c, v);
+    }
+  }
+  if (p.ln2_g == nullptr || !row_ok) return;
+  const float m2 = t1 * invn;
+  const float mean2 = shift2 + m2;
+  const float rstd2 = 1.0f / sqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 16) {
+    float v[16];
+    load_c(c, v);                     // y, as stored in sweep 2
+    affine16(v, mean2, rstd2, p.ln2_g, p.ln2_b, c);
+    store16(p.C2 + row_off + c, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 template <int EPI, int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -301,12 +412,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         row_off = (((size_t)b * p.T2 + t2) * p.F2 + f2) * p.ldc;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if constexpr (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2 || EPI == EPI_BIAS_LN) {
+        epilogue_ln<EPI, BLOCK_N>(p, taddr, row_ok, row_off);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane takes part even if its row is masked
-        const int n = nt * BLOCK_N + c;
-        if (row_ok && n < p.N) epilogue_store16<EPI>(p, v, row_off, n);
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane takes part even if its row is masked
+          const int n = nt * BLOCK_N + c;
+          if (row_ok && n < p.N) epilogue_store16<EPI>(p, v, row_off, n);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -368,6 +483,9 @@ int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorM
     case EPI_GLU: return launch_one<EPI_GLU, BLOCK_N>(ctx, ma, mb, tp, s);
     case EPI_RESID: return launch_one<EPI_RESID, BLOCK_N>(ctx, ma, mb, tp, s);
     case EPI_NONE: return launch_one<EPI_NONE, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_RESID_LN: return launch_one<EPI_RESID_LN, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_RESID_LN2: return launch_one<EPI_RESID_LN2, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_BIAS_LN: return launch_one<EPI_BIAS_LN, BLOCK_N>(ctx, ma, mb, tp, s);
   }
   snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: bad epilogue %d", epi);
   return 1;
@@ -415,6 +533,11 @@ int tc_init(TcContext* ctx) {
 bool tc_gemm_supported(const GemmParams& p, int epilogue) {
   if (p.M <= 0 || p.N % 4 != 0 || p.K % 4 != 0) return false;
   if (epilogue == EPI_GLU && p.N % 8 != 0) return false;
+  if (epilogue >= EPI_RESID_LN) {
+    // fused LayerNorm: the row must be exactly one instantiated tile width, plain A operand, bias present
+    if (p.a_mode != 0 || p.bias == nullptr || p.C2 == nullptr || p.ln1_g == nullptr || p.N != p.ldc) return false;
+    if (!(p.N == 64 || p.N == 128 || p.N == 144 || p.N == 192 || p.N == 256)) return false;
+  }
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W) | reinterpret_cast<uintptr_t>(p.C)) & 15) return false;
   if (p.a_mode == 0) return (p.lda % 4) == 0;
   return p.F2 <= 64 && p.F2 >= 1 && (BLOCK_M / p.F2) >= 1 && (p.D % 4) == 0 && p.N == p.D && 2 * p.F2 <= 256;
@@ -425,9 +548,10 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: tensor-map encoder not initialised");
     return 1;
   }
-  const int bn = pick_block_n(p.N);
+  const int bn = (epilogue >= EPI_RESID_LN) ? p.N : pick_block_n(p.N);
   TcParams tp{};
   tp.bias = p.bias; tp.resid = p.resid; tp.C = p.C; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.ldc = p.ldc; tp.alpha = p.alpha;
+  tp.ln1_g = p.ln1_g; tp.ln1_b = p.ln1_b; tp.ln2_g = p.ln2_g; tp.ln2_b = p.ln2_b; tp.C2 = p.C2; tp.ln_eps = p.ln_eps;
   tp.num_n_tiles = ceil_div(p.N, bn);
   tp.a_mode = p.a_mode;
   CUtensorMap ma, mb;

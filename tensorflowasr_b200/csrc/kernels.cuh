@@ -38,6 +38,10 @@ enum Epilogue : int {
   EPI_GLU = 3,         // C[:, j] = (acc[2j]+b[2j]) * sigmoid(acc[2j+1]+b[2j+1])   (weights pre-interleaved), ldc = N/2
   EPI_RESID = 4,       // C = resid + alpha * (acc + bias)
   EPI_NONE = 5,        // C = acc
+  // fused LayerNorm epilogues (tcgen05 path only; need the whole row in one tile: N <= 256)
+  EPI_RESID_LN = 6,    // x = resid + alpha*(acc+bias) -> C;  LN(x; ln1) -> C2
+  EPI_RESID_LN2 = 7,   // y = LN(resid + alpha*(acc+bias); ln1) -> C;  LN(y; ln2) -> C2 (skipped when ln2_g == null)
+  EPI_BIAS_LN = 8,     // x = acc + bias -> C;  LN(x; ln1) -> C2
 };
 
 struct GemmParams {
@@ -48,6 +52,10 @@ struct GemmParams {
   float* C;            // [M, ldc]
   int M, N, K, lda, ldc;
   float alpha;
+  // fused LayerNorm epilogues
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  float* C2 = nullptr;  // [M, ldc]
+  float ln_eps = 1e-3f;
   // implicit-GEMM geometry for the second subsampling conv (3x3, stride 2, TF 'same')
   int a_mode;          // 0 plain, 1 conv2 im2col
   int T1, F1, T2, F2, D, pad_t, pad_f;

@@ -64,6 +64,7 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_time_stage.argtypes = [vp, ci, ci, ci, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_double)]
     lib.b200asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, vp]
+    lib.b200asr_debug_gemm_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, ci, vp, vp, vp, vp, cf, vp]
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib
@@ -248,6 +249,19 @@ class Engine:
                                                 float(alpha), int(epilogue), int(bool(tensor_cores)), self._stream()),
                     "b200asr_debug_gemm")
         return C
+
+    def debug_gemm_ln(self, A, Wt, bias, resid, alpha, epilogue, ln1, ln2=None, eps=1e-3, inplace=False):
+        """Test hook: fused-LayerNorm epilogues of the tcgen05 kernel.  Returns (C, C2)."""
+        torch = _torch()
+        M, K = A.shape
+        N = Wt.shape[0]
+        C = resid if (inplace and resid is not None) else torch.empty((M, N), device=self._dev(), dtype=torch.float32)
+        C2 = torch.zeros((M, N), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_debug_gemm_ln(
+            self._h, A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), resid.data_ptr() if resid is not None else None, C.data_ptr(),
+            C2.data_ptr(), M, N, K, float(alpha), int(epilogue), ln1[0].data_ptr(), ln1[1].data_ptr(),
+            ln2[0].data_ptr() if ln2 else None, ln2[1].data_ptr() if ln2 else None, float(eps), self._stream()), "b200asr_debug_gemm_ln")
+        return C, C2
 
     STAGES = {"conv2": 0, "ffn_w1": 1, "ffn_w2": 2, "stft": 3, "sub_linear": 4, "attention": 5, "ctc_fc": 6}
 
