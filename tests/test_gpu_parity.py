@@ -260,3 +260,33 @@ def test_abi_argument_errors(eng32, torch_mod):
     assert lib.b200asr_ctc_beam(h, x.data_ptr(), None, 1, 1, 4, 3, 99, 40, 1.0, x.data_ptr(), x.data_ptr(), x.data_ptr(), None) != 0
     assert b"beam size" in lib.b200asr_last_error(h)
     assert lib.b200asr_recognize(h, x.data_ptr(), 0, 100, x.data_ptr(), x.data_ptr(), None) == 0   # empty batch is a no-op
+
+
+def test_reference_facing_asr_surface(ref_wav):
+    """ASR(config).compile(dir).stt(wav) -- the call sequence of Inference/PythonInference/asr/src/asr.py / test_asr.py."""
+    from oracle import ort_ref
+    from tensorflowasr_b200 import asr as A
+    vocab = os.path.join(ort_ref.REF_DIR, "dict", "pinyin.txt")
+    if not os.path.isfile(vocab) or ort_ref.model_dir("offline") is None:
+        pytest.skip("reference vocabulary / models not staged")
+    cfg = {"running_config": {}, "optimizer_config": {}, "tar_config": None,
+           "speech_config": {"sample_rate": 16000, "frame_ms": 25, "stride_ms": 10, "num_feature_bins": 80, "streaming": False,
+                             "streaming_bucket": 0.5},
+           "model_config": {"dmodel": 144, "num_blocks": 13, "num_heads": 4, "head_size": 36, "kernel_size": 32},
+           "inp_config": {"vocabulary": vocab, "blank_at_zero": False, "beam_width": 1}}
+    a = A.ASR(cfg)
+    a.compile(ort_ref.model_dir("offline"))
+    wav_path = os.path.join(os.path.dirname(__file__), "golden", "BAC009S0764W0121.wav")
+    phones, text = a.stt(wav_path)
+    assert phones.split(" ") == a.phone_featurizer.iextract(GOLDEN_IDS) and text == ""
+    feat = a.extract_feature(ref_wav)
+    assert feat.shape == (1, 106, 144) and feat.dtype == np.float32
+    assert a.decode([feat]) == phones
+    assert a.decode([feat[:, :50], feat[:, 50:]]) == phones               # hstack along time (asr.py:65-66)
+    logits = a.engine.ctc_logits(feat).cpu().numpy()[0]
+    assert a.greedy_decode(a.softmax(logits), 1331) == GOLDEN_IDS
+    cfg["inp_config"]["beam_width"] = 8                                   # the YAML key the reference never reads
+    b = A.ASR(cfg)
+    b.compile(ort_ref.model_dir("offline"))
+    assert b.stt(wav_path)[0] == phones
+    assert a.recognize_batch(np.stack([ref_wav[:30000], ref_wav[:30000]]))[0] == a.recognize_batch(ref_wav[None, :30000])[0]
