@@ -123,6 +123,11 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
                                       float* C, float* C2, int M, int N, int K, float alpha, int epilogue, const float* ln1_g,
                                       const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream);
 
+/* Test hook: softmax(Q K^T) V per head on qkv [B*T, 3*H*dh] (q | k | v, head-major, q pre-scaled) -> out [B*T, H*dh];
+ * win_front < 0 = full attention, else the ChunkConformer band.  tcgen05 kernel (1) or fp32 CUDA-core kernel (0). */
+B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, float* out, int B, int T, int H, int dh,
+                                        int win_front, int win_back, int use_tensor_cores, void* stream);
+
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
 

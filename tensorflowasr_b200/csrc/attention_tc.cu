@@ -1,0 +1,363 @@
+// Multi-head self-attention on the 5th-gen tensor cores (tcgen05, tf32 inputs, fp32 accumulate in TMEM).
+//
+// Reference semantics: MultiHeadAttention.call (asr/models/layers/multihead_attention.py:151-188): softmax(Q K^T) V per head,
+// no mask, no positional term, 1/sqrt(d) already folded into Wq.  One CTA = (batch, head, 128 queries):
+//   * Q [128 x d], K [256 x d] and V^T [d x 256] tiles are written by the CTA's threads straight into the canonical
+//     K-major SWIZZLE_128B shared-memory layout (rounded to nearest tf32, zero padded to 64 columns / masked rows), so no
+//     padded copy of the QKV activations is ever needed in HBM;
+//   * S = Q K^T: 8 x tcgen05.mma (M=128, N=256, K=8) into TMEM columns [0,256);
+//   * softmax: thread == query row; the row is swept from TMEM twice (max, then exp / sum); P is written back IN PLACE
+//     over S with tcgen05.st (tf32-truncated, and the row sum is taken over the truncated values so the truncation
+//     cancels in the normalisation);
+//   * O_blk = P V: 32 x tcgen05.mma with the A operand read from TMEM (TS form), B = V^T from shared memory, into TMEM
+//     columns [256,320); the running output is kept in registers with the usual online-softmax rescale, so longer
+//     sequences simply loop over 256-key blocks.
+// An optional band (chunk_conformer_blocks.py:158-176) restricts the visible keys per query.
+#include "kernels.cuh"
+
+namespace b200asr {
+
+namespace {
+
+constexpr int kQT = 128;     // queries per CTA
+constexpr int kKT = 256;     // keys per block
+constexpr int kDP = 64;      // head dim padded to two 32-float swizzle slabs
+constexpr int kThreadsA = 384;     // warps 0-3: softmax rows (thread == query), warp 4: MMA issue + TMEM, all 12: tile staging
+constexpr unsigned kSpin = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float to_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mbar_init_a(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32a(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait_a(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32a(bar);
+  unsigned spins = 0;
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > kSpin) {
+      printf("b200asr attention_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void commit_a(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32a(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B tile made of 32-float slabs of `rows` rows each
+__device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows) {
+  const int slab = k >> 5, kk = k & 31;
+  return (uint32_t)(slab * rows * 128 + row * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2)));
+}
+
+__global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qs = smem;                                  // 2 slabs x 128 rows x 128 B = 32 KB
+  uint8_t* Ks = Qs + 2 * kQT * 128;                    // 2 slabs x 256 rows x 128 B = 64 KB
+  uint8_t* Vt = Ks + 2 * kKT * 128;                    // 8 slabs x  64 rows x 128 B = 64 KB   (V transposed: rows = head dim)
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(Vt + 8 * kDP * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int dh = p.dh, ld = 3 * p.H * dh;
+  const float* base = p.qkv + (size_t)b * p.T * ld;
+  const float* qbase = base + h * dh;
+  const float* kbase = base + p.H * dh + h * dh;
+  const float* vbase = base + 2 * p.H * dh + h * dh;
+
+  if (tid == 0) {
+    mbar_init_a(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32a(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;            // columns [0, 256)
+  const uint32_t tmem_O = tmem_base + kKT;      // columns [256, 320)
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t phase = 0;
+  const bool single_block = (p.T <= kKT);       // K / V^T staged once and reused by every query tile of this CTA
+  bool kv_loaded = false;
+
+  // staging helpers: 4 independent 16-byte loads in flight per thread before the first shared-memory store
+  auto stage_rows = [&](uint8_t* dst, const float* src, int row0, int rows) {   // row-major tile -> K-major SW128 (Q, K)
+    for (int i0 = tid; i0 < rows * (kDP / 4); i0 += 4 * kThreadsA) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreadsA;
+        const int r = i >> 4, c4 = i & 15;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < rows * (kDP / 4) && row0 + r < p.T && 4 * c4 < dh)
+          v[u] = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + 4 * c4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreadsA;
+        if (i < rows * (kDP / 4)) {
+          const int r = i >> 4, c4 = i & 15;
+          float4 w = v[u];
+          w.x = to_tf32_rn(w.x); w.y = to_tf32_rn(w.y); w.z = to_tf32_rn(w.z); w.w = to_tf32_rn(w.w);
+          *reinterpret_cast<float4*>(dst + sw128_off(r, 4 * c4, rows)) = w;
+        }
+      }
+    }
+  };
+  auto stage_vt = [&](int k0) {                                                 // V [key][d] -> V^T [d][key] K-major SW128
+    for (int i0 = tid; i0 < kKT * (kDP / 4); i0 += 4 * kThreadsA) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreadsA;
+        const int key = i & (kKT - 1), c4 = i >> 8;   // key fastest: conflict-free transposed stores
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < kKT * (kDP / 4) && k0 + key < p.T && 4 * c4 < dh)
+          v[u] = *reinterpret_cast<const float4*>(vbase + (size_t)(k0 + key) * ld + 4 * c4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreadsA;
+        if (i < kKT * (kDP / 4)) {
+          const int key = i & (kKT - 1), c4 = i >> 8;
+          *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 0, key, kDP)) = to_tf32_rn(v[u].x);
+          *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 1, key, kDP)) = to_tf32_rn(v[u].y);
+          *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 2, key, kDP)) = to_tf32_rn(v[u].z);
+          *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 3, key, kDP)) = to_tf32_rn(v[u].w);
+        }
+      }
+    }
+  };
+
+  for (int q0 = blockIdx.x * kQT; q0 < p.T; q0 += gridDim.x * kQT) {
+  stage_rows(Qs, qbase, q0, kQT);               // rows beyond T and columns beyond dh are zero
+
+  // per-row state (threads 0..127: thread == query row)
+  const int qi = q0 + tid;
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[kDP];
+#pragma unroll
+  for (int d = 0; d < kDP; ++d) o[d] = 0.f;
+  int lo = 0, hi = p.T - 1;
+  if (p.win_front >= 0) {
+    lo = max(min(max(qi - p.win_front, 0), p.T - p.win_back), 0);
+    hi = min(max(min(qi + p.win_back, p.T), p.win_back), p.T - 1);
+  }
+
+  for (int k0 = 0; k0 < p.T; k0 += kKT) {
+    // ---- stage K [256 x 64] and V^T [64 x 256] for this key block
+    if (!(single_block && kv_loaded)) {
+      stage_rows(Ks, kbase, k0, kKT);
+      stage_vt(k0);
+      kv_loaded = true;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+    fence_before();
+    __syncthreads();
+    // ---- S = Q K^T
+    if (warp == 4) {
+      fence_after();
+      if (lane == 0) {
+        const uint32_t qa = smem_u32a(Qs), ka = smem_u32a(Ks);
+        const int ksteps = (dh + 7) / 8;               // only k-steps that hold real data (rest is zero padding)
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = smem_desc_sw128(qa + (ks >> 2) * (kQT * 128) + (ks & 3) * 32);
+          const uint64_t db = smem_desc_sw128(ka + (ks >> 2) * (kKT * 128) + (ks & 3) * 32);
+          mma_ss(tmem_S, da, db, idesc_tf32(kQT, kKT), ks > 0 ? 1u : 0u);
+        }
+        commit_a(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait_a(mma_bar, phase);
+    phase ^= 1;
+    fence_after();
+    // ---- softmax over this block's keys, P written back in place
+    float corr = 1.f;
+    if (warp < 4) {
+      const int nk = min(kKT, p.T - k0);
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kKT; c += 32) {
+        if (c >= nk) break;                            // warp-uniform: whole chunk beyond the sequence
+        uint32_t r[32];
+        tmem_ld32(tmem_S + lane_addr + (uint32_t)c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = k0 + c + j;
+          if (c + j < nk && key >= lo && key <= hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const bool any = (m_new != -INFINITY);
+      corr = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+      if (!any) corr = 1.f;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kKT; c += 32) {
+        if (c >= ((nk + 7) & ~7)) break;               // P columns at or beyond ceil8(nk) are never read by the P.V MMAs
+        uint32_t r[32];
+        tmem_ld32(tmem_S + lane_addr + (uint32_t)c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = k0 + c + j;
+          float pv = 0.f;
+          if (any && c + j < nk && key >= lo && key <= hi) pv = __expf(__uint_as_float(r[j]) - m_new);
+          const uint32_t pt = __float_as_uint(pv) & 0xFFFFE000u;   // what the tf32 datapath will see
+          sum += __uint_as_float(pt);
+          r[j] = pt;
+        }
+        tmem_st32(tmem_S + lane_addr + (uint32_t)c, r);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      l_run = l_run * corr + sum;
+      m_run = m_new;
+    }
+    fence_before();
+    __syncthreads();
+    // ---- O_blk = P V   (A from TMEM)
+    if (warp == 4) {
+      fence_after();
+      if (lane == 0) {
+        const uint32_t va = smem_u32a(Vt);
+        const int nk = min(kKT, p.T - k0);
+        const int ksteps = (nk + 7) / 8;               // keys beyond nk have P == 0 and V^T == 0
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t db = smem_desc_sw128(va + (ks >> 2) * (kDP * 128) + (ks & 3) * 32);
+          mma_ts(tmem_O, tmem_S + (uint32_t)(8 * ks), db, idesc_tf32(kQT, kDP), ks > 0 ? 1u : 0u);
+        }
+        commit_a(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait_a(mma_bar, phase);
+    phase ^= 1;
+    fence_after();
+    if (warp < 4) {
+#pragma unroll
+      for (int c = 0; c < kDP; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_O + lane_addr + (uint32_t)c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[c + j] = o[c + j] * corr + __uint_as_float(r[j]);
+      }
+    }
+    fence_before();
+    __syncthreads();   // S/P, O_blk and the Q/K/V tiles may be overwritten next
+    fence_after();
+  }
+
+  if (warp < 4 && qi < p.T) {
+    const float inv = 1.0f / l_run;
+    float* orow = p.out + ((size_t)b * p.T + qi) * (p.H * dh) + h * dh;
+#pragma unroll
+    for (int c4 = 0; c4 < kDP / 4; ++c4) {
+      if (4 * c4 < dh)
+        *reinterpret_cast<float4*>(orow + 4 * c4) =
+            make_float4(o[4 * c4] * inv, o[4 * c4 + 1] * inv, o[4 * c4 + 2] * inv, o[4 * c4 + 3] * inv);
+    }
+  }
+  }  // query tiles
+  fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+bool attention_tc_supported(const AttnParams& p) {
+  return p.dh % 4 == 0 && p.dh <= kDP && p.dh >= 4 && ((p.H * p.dh) % 4) == 0 && p.T > 0;
+}
+
+int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
+  if (p.B == 0 || p.T == 0) return 0;
+  const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + 8 * kDP * 128 + 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  // one CTA per (batch, head) when the whole sequence is a single key block (K / V^T staged once for all query tiles)
+  const int qtiles = ceil_div(p.T, kQT);
+  dim3 grid(p.T <= kKT ? 1 : qtiles, p.H, p.B);
+  attention_tc_kernel<<<grid, kThreadsA, smem, stream>>>(p);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200asr

@@ -235,6 +235,12 @@ int gemm(Ctx& c, const float* A, int lda, const float* W, const float* bias, con
   return launch_gemm_simt(p, epi, c.s);
 }
 
+int attention(Ctx& c, const AttnParams& ap) {
+  c.h->launches++;
+  if (c.h->cfg.precision == B200ASR_PRECISION_TF32 && c.h->tc.ready && attention_tc_supported(ap)) return launch_attention_tc(ap, c.s);
+  return launch_attention(ap, c.s);
+}
+
 int gemm_p(Ctx& c, const GemmParams& p, int epi) {
   c.h->launches++;
   if (c.h->cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(p, epi)) return launch_gemm_tc(c.h->tc, p, epi, c.s);
@@ -273,8 +279,7 @@ int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int
   if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
   AttnParams ap{};
   ap.qkv = b.h; ap.out = b.att; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = -1; ap.win_back = 0;
-  c.h->launches++;
-  if (launch_attention(ap, c.s)) return 1;
+  if (attention(c, ap)) return 1;
   if (gemm_resid_ln(c, b.att, HD, w.mhsa.wo, w.mhsa.bo, 1.0f, b, M, D, w.conv.ln, nullptr, eps)) return 1;
   if (gemm(c, b.xn, D, w.conv.pw1w, w.conv.pw1b, nullptr, 0.f, b.g, D, M, 2 * D, D, EPI_GLU)) return 1;
   DwConvParams dp{};
@@ -308,8 +313,7 @@ int run_block(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, in
   if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
   AttnParams ap{};
   ap.qkv = b.h; ap.out = b.att; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = -1; ap.win_back = 0;
-  c.h->launches++;
-  if (launch_attention(ap, c.s)) return 1;
+  if (attention(c, ap)) return 1;
   if (gemm(c, b.att, HD, w.mhsa.wo, w.mhsa.bo, b.x, 1.0f, b.x, D, M, D, HD, EPI_RESID)) return 1;
   // conv module
   c.h->launches++;
@@ -842,7 +846,7 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
       case B200ASR_STAGE_ATTENTION: {
         AttnParams ap{};
         ap.qkv = b.h; ap.out = b.att; ap.B = s.B; ap.T = s.T2; ap.H = cfg.num_heads; ap.dh = cfg.head_size; ap.win_front = -1;
-        rc = launch_attention(ap, st);
+        rc = attention(c, ap);
         *flops = 4.0 * s.B * cfg.num_heads * (double)s.T2 * s.T2 * cfg.head_size;
         *bytes = 4.0 * (3.0 * M * cfg.num_heads * cfg.head_size + M * cfg.num_heads * cfg.head_size);
         break;
@@ -901,6 +905,22 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
   if (!tc_gemm_supported(p, epilogue)) return fail(h, "b200asr_debug_gemm_ln: shape not supported by the tcgen05 path");
   h->launches++;
   ENG_TRY(h, launch_gemm_tc(h->tc, p, epilogue, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Test hook: one multi-head attention call through the tcgen05 kernel (use_tensor_cores = 1) or the fp32 CUDA-core kernel.
+B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, float* out, int B, int T, int H, int dh, int win_front,
+                            int win_back, int use_tensor_cores, void* stream) {
+  if (!h) return 1;
+  AttnParams ap{};
+  ap.qkv = qkv; ap.out = out; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = win_front; ap.win_back = win_back;
+  h->launches++;
+  if (use_tensor_cores) {
+    if (!attention_tc_supported(ap)) return fail(h, "b200asr_debug_attention: shape not supported by the tcgen05 kernel");
+    ENG_TRY(h, launch_attention_tc(ap, static_cast<cudaStream_t>(stream)));
+  } else {
+    ENG_TRY(h, launch_attention(ap, static_cast<cudaStream_t>(stream)));
+  }
   return 0;
 }
 

@@ -24,7 +24,6 @@ namespace b200asr {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;        // fp32 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;          // tf32
 constexpr int kStages = 4;
@@ -105,17 +104,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -131,6 +119,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// SFU-approximate activations for the tensor-core path (ex2.approx + rcp.approx, ~1e-6 relative: far below tf32 input rounding)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float swish_fast(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ epilogue
 template <int EPI>
@@ -151,10 +152,10 @@ __device__ __forceinline__ void epilogue_store16(const TcParams& p, float* v, si
     for (int q = 0; q < 2; ++q) {
       if (n + 8 * q < p.N) {
         float4 o;
-        o.x = v[8 * q + 0] * sigmoidf_(v[8 * q + 1]);
-        o.y = v[8 * q + 2] * sigmoidf_(v[8 * q + 3]);
-        o.z = v[8 * q + 4] * sigmoidf_(v[8 * q + 5]);
-        o.w = v[8 * q + 6] * sigmoidf_(v[8 * q + 7]);
+        o.x = v[8 * q + 0] * sigmoid_fast(v[8 * q + 1]);
+        o.y = v[8 * q + 2] * sigmoid_fast(v[8 * q + 3]);
+        o.z = v[8 * q + 4] * sigmoid_fast(v[8 * q + 5]);
+        o.w = v[8 * q + 6] * sigmoid_fast(v[8 * q + 7]);
         *reinterpret_cast<float4*>(dst + 4 * q) = o;
       }
     }
@@ -168,7 +169,7 @@ __device__ __forceinline__ void epilogue_store16(const TcParams& p, float* v, si
       if (EPI == EPI_BIAS_RELU) {
         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
       } else if (EPI == EPI_BIAS_SWISH) {
-        o.x = swishf_(o.x); o.y = swishf_(o.y); o.z = swishf_(o.z); o.w = swishf_(o.w);
+        o.x = swish_fast(o.x); o.y = swish_fast(o.y); o.z = swish_fast(o.z); o.w = swish_fast(o.w);
       } else if (EPI == EPI_RESID) {
         const float4 r = *reinterpret_cast<const float4*>(p.resid + row_off + n + 4 * q);
         o.x = r.x + p.alpha * o.x; o.y = r.y + p.alpha * o.y; o.z = r.z + p.alpha * o.z; o.w = r.w + p.alpha * o.w;
@@ -184,58 +185,69 @@ __device__ __forceinline__ void epilogue_store16(const TcParams& p, float* v, si
 // TMEM two (three) times -- statistics (shifted one-pass variance), then normalise -- instead of being parked in registers.
 template <int EPI, int BLOCK_N>
 __device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, bool row_ok, size_t row_off) {
-  const bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
-  auto load_x = [&](int c, float* v) {
-    tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective
+  constexpr bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
+  constexpr int G = (BLOCK_N % 48 == 0) ? 48 : ((BLOCK_N % 32 == 0) ? 32 : 16);   // columns per batch of loads
+  // x[c0 .. c0+G) of this thread's row: accumulator (TMEM) + bias (+ residual).  All G/16 tcgen05.ld and all residual
+  // loads are issued before the first use so their latencies overlap (one exposed L2 round trip per batch, not per chunk).
+  auto load_x = [&](int c0, float* v) {
+    uint32_t raw[G];
+#pragma unroll
+    for (int j = 0; j < G / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16 * j), raw + 16 * j);   // warp-collective
+    float4 rr[G / 4];
+    if (has_resid && row_ok) {
+#pragma unroll
+      for (int q = 0; q < G / 4; ++q) rr[q] = *reinterpret_cast<const float4*>(p.resid + row_off + c0 + 4 * q);
+    }
+    tmem_ld_wait();
     if (!row_ok) return;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + c + 4 * q);
-      v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    for (int q = 0; q < G / 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
+      float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
+      float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
       if (has_resid) {
-        const float4 r = *reinterpret_cast<const float4*>(p.resid + row_off + c + 4 * q);
-        v[4 * q + 0] = r.x + p.alpha * v[4 * q + 0]; v[4 * q + 1] = r.y + p.alpha * v[4 * q + 1];
-        v[4 * q + 2] = r.z + p.alpha * v[4 * q + 2]; v[4 * q + 3] = r.w + p.alpha * v[4 * q + 3];
+        a0 = rr[q].x + p.alpha * a0; a1 = rr[q].y + p.alpha * a1; a2 = rr[q].z + p.alpha * a2; a3 = rr[q].w + p.alpha * a3;
       }
+      v[4 * q + 0] = a0; v[4 * q + 1] = a1; v[4 * q + 2] = a2; v[4 * q + 3] = a3;
     }
   };
   // re-read this thread's own row from C (written earlier by this same thread): needed because C may alias resid
-  auto load_c = [&](int c, float* v) {
+  auto load_c = [&](int c0, float* v) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 r = *reinterpret_cast<const float4*>(p.C + row_off + c + 4 * q);
+    for (int q = 0; q < G / 4; ++q) {
+      const float4 r = *reinterpret_cast<const float4*>(p.C + row_off + c0 + 4 * q);
       v[4 * q + 0] = r.x; v[4 * q + 1] = r.y; v[4 * q + 2] = r.z; v[4 * q + 3] = r.w;
     }
   };
-  auto store16 = [&](float* dst, const float* v) {
+  auto store_g = [&](float* dst, const float* v) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < G / 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   };
-  auto affine16 = [&](float* v, float mean, float rstd, const float* g, const float* be, int c) {
+  auto affine_g = [&](float* v, float mean, float rstd, const float* g, const float* be, int c0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 gg = *reinterpret_cast<const float4*>(g + c + 4 * q);
-      const float4 bb = *reinterpret_cast<const float4*>(be + c + 4 * q);
+    for (int q = 0; q < G / 4; ++q) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c0 + 4 * q));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c0 + 4 * q));
       v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
       v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
     }
   };
   const float invn = 1.0f / (float)BLOCK_N;
-  // sweep 1: x (stored for *_LN modes where C holds the un-normalised stream) + statistics
+  // sweep 1: x (stored for *_LN modes where C holds the un-normalised stream) + statistics (shifted one-pass variance)
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += 16) {
-    float v[16];
+  for (int c = 0; c < BLOCK_N; c += G) {
+    float v[G];
     load_x(c, v);
-    if (c == 0) shift = v[0];
     if (row_ok) {
+      if (c == 0) shift = v[0];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < G; ++i) {
         const float d = v[i] - shift;
         s1 += d;
         s2 = fmaf(d, d, s2);
       }
-      if (EPI != EPI_RESID_LN2) store16(p.C + row_off + c, v);
+      if (EPI != EPI_RESID_LN2) store_g(p.C + row_off + c, v);
     }
   }
   const float m1 = s1 * invn;
@@ -245,32 +257,30 @@ __device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, b
     // sweep 2: LN(x; ln1) -> C2   (x read back from C: the residual operand may have been overwritten in place)
     if (!row_ok) return;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
-      float v[16];
+    for (int c = 0; c < BLOCK_N; c += G) {
+      float v[G];
       load_c(c, v);
-      {
-        affine16(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
-        store16(p.C2 + row_off + c, v);
-      }
+      affine_g(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
+      store_g(p.C2 + row_off + c, v);
     }
     return;
   }
   // EPI_RESID_LN2: sweep 2: y = LN(x; ln1) -> C, statistics of y; sweep 3: LN(y; ln2) -> C2
   float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += 16) {
-    float v[16];
+  for (int c = 0; c < BLOCK_N; c += G) {
+    float v[G];
     load_x(c, v);
     if (row_ok) {
-      affine16(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
+      affine_g(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
       if (c == 0) shift2 = v[0];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < G; ++i) {
         const float d = v[i] - shift2;
         t1 += d;
         t2 = fmaf(d, d, t2);
       }
-      store16(p.C + row_off + c, v);
+      store_g(p.C + row_off + c, v);
     }
   }
   if (p.ln2_g == nullptr || !row_ok) return;
@@ -278,16 +288,16 @@ __device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, b
   const float mean2 = shift2 + m2;
   const float rstd2 = 1.0f / sqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
 #pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += 16) {
-    float v[16];
+  for (int c = 0; c < BLOCK_N; c += G) {
+    float v[G];
     load_c(c, v);                     // y, as stored in sweep 2
-    affine16(v, mean2, rstd2, p.ln2_g, p.ln2_b, c);
-    store16(p.C2 + row_off + c, v);
+    affine_g(v, mean2, rstd2, p.ln2_g, p.ln2_b, c);
+    store_g(p.C2 + row_off + c, v);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int EPI, int BLOCK_N>
+template <int EPI, int BLOCK_N, int BLOCK_M>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -390,7 +400,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;         // row inside the 128-row tile
+    // accumulator row held by this thread: M=128 fills all 128 lanes; M=64 uses lanes 0..15 of each quadrant
+    // (cute tmem_frg: (16,4) x N with lane strides (1,32))
+    const int r = (BLOCK_M == 128) ? quad * 32 + lane : quad * 16 + (lane & 15);
+    const bool lane_ok = (BLOCK_M == 128) || lane < 16;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -402,25 +415,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       size_t row_off;
       if (p.a_mode == 0) {
         const int m = mt * BLOCK_M + r;
-        row_ok = m < p.M;
+        row_ok = lane_ok && m < p.M;
         row_off = (size_t)m * p.ldc;
       } else {
         const int b = mt / p.tiles_per_b, tb = mt - b * p.tiles_per_b;
         const int i = r / p.F2, f2 = r - i * p.F2;
         const int t2 = tb * p.bt + i;
-        row_ok = (i < p.bt) && (t2 < p.T2);
+        row_ok = lane_ok && (i < p.bt) && (t2 < p.T2);
         row_off = (((size_t)b * p.T2 + t2) * p.F2 + f2) * p.ldc;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if constexpr (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2 || EPI == EPI_BIAS_LN) {
         epilogue_ln<EPI, BLOCK_N>(p, taddr, row_ok, row_off);
       } else {
+        constexpr int G = (BLOCK_N % 48 == 0) ? 48 : ((BLOCK_N % 32 == 0) ? 32 : 16);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 16) {
-          float v[16];
-          tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane takes part even if its row is masked
-          const int n = nt * BLOCK_N + c;
-          if (row_ok && n < p.N) epilogue_store16<EPI>(p, v, row_off, n);
+        for (int c = 0; c < BLOCK_N; c += G) {
+          uint32_t raw[G];
+#pragma unroll
+          for (int j = 0; j < G / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c + 16 * j), raw + 16 * j);   // warp-collective
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < G / 16; ++j) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[16 * j + i]);
+            const int n = nt * BLOCK_N + c + 16 * j;
+            if (row_ok && n < p.N) epilogue_store16<EPI>(p, v, row_off, n);
+          }
         }
       }
       tcgen05_fence_before();
@@ -454,38 +476,38 @@ int encode_map(TcContext& ctx, CUtensorMap* map, const void* base, int rank, con
   return 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_M>
 constexpr size_t smem_bytes() {
   return (size_t)kStages * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-template <int EPI, int BLOCK_N>
+template <int EPI, int BLOCK_N, int BLOCK_M>
 int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<EPI, BLOCK_N>;
+  auto kern = gemm_tc_kernel<EPI, BLOCK_N, BLOCK_M>;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BLOCK_N>()));
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BLOCK_N, BLOCK_M>()));
     configured = true;
   }
   const int tiles = tp.num_m_tiles * tp.num_n_tiles;
   const int grid = tiles < ctx.num_sms ? tiles : ctx.num_sms;
-  kern<<<grid, kThreads, smem_bytes<BLOCK_N>(), stream>>>(ma, mb, tp);
+  kern<<<grid, kThreads, smem_bytes<BLOCK_N, BLOCK_M>(), stream>>>(ma, mb, tp);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_M>
 int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS: return launch_one<EPI_BIAS, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_BIAS_RELU: return launch_one<EPI_BIAS_RELU, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_BIAS_SWISH: return launch_one<EPI_BIAS_SWISH, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_GLU: return launch_one<EPI_GLU, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_RESID: return launch_one<EPI_RESID, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_NONE: return launch_one<EPI_NONE, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_RESID_LN: return launch_one<EPI_RESID_LN, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_RESID_LN2: return launch_one<EPI_RESID_LN2, BLOCK_N>(ctx, ma, mb, tp, s);
-    case EPI_BIAS_LN: return launch_one<EPI_BIAS_LN, BLOCK_N>(ctx, ma, mb, tp, s);
+    case EPI_BIAS: return launch_one<EPI_BIAS, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_BIAS_RELU: return launch_one<EPI_BIAS_RELU, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_BIAS_SWISH: return launch_one<EPI_BIAS_SWISH, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_GLU: return launch_one<EPI_GLU, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_RESID: return launch_one<EPI_RESID, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_NONE: return launch_one<EPI_NONE, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_RESID_LN: return launch_one<EPI_RESID_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_RESID_LN2: return launch_one<EPI_RESID_LN2, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_BIAS_LN: return launch_one<EPI_BIAS_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
   }
   snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: bad epilogue %d", epi);
   return 1;
@@ -540,7 +562,7 @@ bool tc_gemm_supported(const GemmParams& p, int epilogue) {
   }
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W) | reinterpret_cast<uintptr_t>(p.C)) & 15) return false;
   if (p.a_mode == 0) return (p.lda % 4) == 0;
-  return p.F2 <= 64 && p.F2 >= 1 && (BLOCK_M / p.F2) >= 1 && (p.D % 4) == 0 && p.N == p.D && 2 * p.F2 <= 256;
+  return p.F2 <= 64 && p.F2 >= 1 && (128 / p.F2) >= 1 && (p.D % 4) == 0 && p.N == p.D && 2 * p.F2 <= 256;
 }
 
 int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream_t stream) {
@@ -562,17 +584,20 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
     if (encode_map(ctx, &mb, p.W, 2, dims, strides, box, ones)) return 1;
   }
+  // M tile: 128 rows normally; 64 when 128-row tiles would leave most SMs idle (the 8000-row, N<=256 GEMMs of one batch)
+  int bm = 128;
+  if (p.a_mode == 0 && ceil_div(p.M, 128) * tp.num_n_tiles < (ctx.num_sms * 3) / 4) bm = 64;
   if (p.a_mode == 0) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 4};
-    const cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bm};
     if (encode_map(ctx, &ma, p.A, 2, dims, strides, box, ones)) return 1;
-    tp.num_m_tiles = ceil_div(p.M, BLOCK_M);
+    tp.num_m_tiles = ceil_div(p.M, bm);
     tp.num_k_blocks = ceil_div(p.K, BLOCK_K);
   } else {
     const int B = p.M / (p.T2 * p.F2);
     tp.T2 = p.T2; tp.F2 = p.F2; tp.D = p.D; tp.pad_t = p.pad_t; tp.pad_f = p.pad_f;
-    tp.bt = BLOCK_M / p.F2;
+    tp.bt = 128 / p.F2;
     tp.kc = ceil_div(p.D, BLOCK_K);
     tp.tiles_per_b = ceil_div(p.T2, tp.bt);
     tp.num_m_tiles = B * tp.tiles_per_b;
@@ -583,12 +608,21 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     const cuuint32_t estr[4] = {1, 2, 2, 1};
     if (encode_map(ctx, &ma, p.A, 4, dims, strides, box, estr)) return 1;
   }
+  if (bm == 64) {
+    switch (bn) {
+      case 64: return dispatch_epi<64, 64>(ctx, epilogue, ma, mb, tp, stream);
+      case 128: return dispatch_epi<128, 64>(ctx, epilogue, ma, mb, tp, stream);
+      case 144: return dispatch_epi<144, 64>(ctx, epilogue, ma, mb, tp, stream);
+      case 192: return dispatch_epi<192, 64>(ctx, epilogue, ma, mb, tp, stream);
+      default: return dispatch_epi<256, 64>(ctx, epilogue, ma, mb, tp, stream);
+    }
+  }
   switch (bn) {
-    case 64: return dispatch_epi<64>(ctx, epilogue, ma, mb, tp, stream);
-    case 128: return dispatch_epi<128>(ctx, epilogue, ma, mb, tp, stream);
-    case 144: return dispatch_epi<144>(ctx, epilogue, ma, mb, tp, stream);
-    case 192: return dispatch_epi<192>(ctx, epilogue, ma, mb, tp, stream);
-    default: return dispatch_epi<256>(ctx, epilogue, ma, mb, tp, stream);
+    case 64: return dispatch_epi<64, 128>(ctx, epilogue, ma, mb, tp, stream);
+    case 128: return dispatch_epi<128, 128>(ctx, epilogue, ma, mb, tp, stream);
+    case 144: return dispatch_epi<144, 128>(ctx, epilogue, ma, mb, tp, stream);
+    case 192: return dispatch_epi<192, 128>(ctx, epilogue, ma, mb, tp, stream);
+    default: return dispatch_epi<256, 128>(ctx, epilogue, ma, mb, tp, stream);
   }
 }
 

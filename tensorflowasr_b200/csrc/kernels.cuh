@@ -73,7 +73,9 @@ struct AttnParams {
   // optional band mask (ChunkConformer, chunk_conformer_blocks.py:158-176); win_front < 0 => full attention
   int win_front, win_back;
 };
-int launch_attention(const AttnParams& p, cudaStream_t stream);
+int launch_attention(const AttnParams& p, cudaStream_t stream);          // fp32 CUDA cores (block_ops.cu)
+bool attention_tc_supported(const AttnParams& p);
+int launch_attention_tc(const AttnParams& p, cudaStream_t stream);       // tcgen05 tf32 (attention_tc.cu)
 
 struct DwConvParams {
   const float* x;   // [B*T, D]

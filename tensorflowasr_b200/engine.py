@@ -65,6 +65,7 @@ def load_library() -> ctypes.CDLL:
                                        ctypes.POINTER(ctypes.c_double)]
     lib.b200asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, vp]
     lib.b200asr_debug_gemm_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, ci, vp, vp, vp, vp, cf, vp]
+    lib.b200asr_debug_attention.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib
@@ -262,6 +263,14 @@ class Engine:
             C2.data_ptr(), M, N, K, float(alpha), int(epilogue), ln1[0].data_ptr(), ln1[1].data_ptr(),
             ln2[0].data_ptr() if ln2 else None, ln2[1].data_ptr() if ln2 else None, float(eps), self._stream()), "b200asr_debug_gemm_ln")
         return C, C2
+
+    def debug_attention(self, qkv, B, T, H, dh, tensor_cores=True, win_front=-1, win_back=0):
+        """Test hook: qkv [B*T, 3*H*dh] (torch cuda) -> attention output [B*T, H*dh]."""
+        torch = _torch()
+        out = torch.empty((B * T, H * dh), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_debug_attention(self._h, qkv.data_ptr(), out.data_ptr(), B, T, H, dh, int(win_front),
+                                                     int(win_back), int(bool(tensor_cores)), self._stream()), "b200asr_debug_attention")
+        return out
 
     STAGES = {"conv2": 0, "ffn_w1": 1, "ffn_w2": 2, "stft": 3, "sub_linear": 4, "attention": 5, "ctc_fc": 6}
 
