@@ -128,6 +128,13 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
 B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, float* out, int B, int T, int H, int dh,
                                         int win_front, int win_back, int use_tensor_cores, void* stream);
 
+/* Test hook: C/C2 = LN-epilogue(resid + alpha * (swish(X.W1^T + b1).W2^T + b2)) through the chained tcgen05 kernel
+ * (hidden activations stay in TMEM).  X [M,K1], W1 [N1,K1], W2 [N2,N1]; epilogue 6 or 7 (see b200asr_debug_gemm_ln). */
+B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const float* W1, const float* b1, const float* W2,
+                                    const float* b2, const float* resid, float* C, float* C2, int M, int K1, int N1, int N2,
+                                    float alpha, int epilogue, const float* ln1_g, const float* ln1_b, const float* ln2_g,
+                                    const float* ln2_b, float eps, void* stream);
+
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
 

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -61,6 +62,7 @@ struct b200asr_engine {
   std::map<GraphKey, int64_t> graph_launches;
   int64_t launches = 0;
   std::string err;
+  bool use_chain = true;   // chained FFN / conv-tail kernel (B200ASR_NO_CHAIN=1 in the environment turns it off)
   void* beam_ws = nullptr;
   size_t beam_ws_bytes = 0;
   cudaStream_t own_stream = nullptr;
@@ -269,13 +271,29 @@ int gemm_resid_ln(Ctx& c, const float* A, int K, const float* W, const float* bi
   return gemm_p(c, p, ln2 ? EPI_RESID_LN2 : EPI_RESID_LN);
 }
 
+// x = x + alpha * (swish(X.W1^T + b1).W2^T + b2) with the LayerNorm epilogue(s), as ONE chained kernel when supported,
+// else as two GEMMs through the wide scratch buffer b.h.
+int chain_resid_ln(Ctx& c, const float* X, int K1, const float* W1, const float* b1, int N1, const float* W2, const float* b2, float alpha,
+                   const Buffers& b, int M, int D, const LNW& ln1, const LNW* ln2, float eps) {
+  ChainGemmParams cp{};
+  cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = b.x; cp.C = b.x; cp.C2 = b.xn; cp.M = M; cp.K1 = K1;
+  cp.N1 = N1; cp.N2 = D; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1.g; cp.ln1_b = ln1.b; cp.ln_eps = eps;
+  if (ln2) { cp.ln2_g = ln2->g; cp.ln2_b = ln2->b; }
+  const int epi = ln2 ? EPI_RESID_LN2 : EPI_RESID_LN;
+  if (c.h->use_chain && tc_chain_supported(cp, epi)) {
+    c.h->launches++;
+    return launch_gemm_chain(c.h->tc, cp, epi, c.s);
+  }
+  if (gemm(c, X, K1, W1, b1, nullptr, 0.f, b.h, N1, M, N1, K1, EPI_BIAS_SWISH)) return 1;
+  return gemm_resid_ln(c, b.h, N1, W2, b2, alpha, b, M, D, ln1, ln2, eps);
+}
+
 // One ConformerBlock with every LayerNorm folded into the epilogue of the GEMM that produces its input (11 launches).
 // Pre-condition: b.xn == LN(b.x; w.ffn1.ln).  Post-condition: b.x = block output, b.xn = LN(b.x; *next_ln) if next_ln.
 int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, int F, int H, int dh, float eps,
                     const LNW* next_ln) {
   const int M = B * T, HD = H * dh;
-  if (gemm(c, b.xn, D, w.ffn1.w1, w.ffn1.b1, nullptr, 0.f, b.h, F, M, F, D, EPI_BIAS_SWISH)) return 1;
-  if (gemm_resid_ln(c, b.h, F, w.ffn1.w2, w.ffn1.b2, 0.5f, b, M, D, w.mhsa.ln, nullptr, eps)) return 1;
+  if (chain_resid_ln(c, b.xn, D, w.ffn1.w1, w.ffn1.b1, F, w.ffn1.w2, w.ffn1.b2, 0.5f, b, M, D, w.mhsa.ln, nullptr, eps)) return 1;
   if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
   AttnParams ap{};
   ap.qkv = b.h; ap.out = b.att; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = -1; ap.win_back = 0;
@@ -287,11 +305,9 @@ int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int
   dp.pad_left = same_pad(T, w.kernel_size, 1).before;
   c.h->launches++;
   if (launch_dwconv(dp, c.s)) return 1;
-  if (gemm(c, b.att, D, w.conv.pww, w.conv.pwb, nullptr, 0.f, b.h, 2 * D, M, 2 * D, D, EPI_BIAS_SWISH)) return 1;
-  if (gemm_resid_ln(c, b.h, 2 * D, w.conv.pw2w, w.conv.pw2b, 1.0f, b, M, D, w.ffn2.ln, nullptr, eps)) return 1;
-  if (gemm(c, b.xn, D, w.ffn2.w1, w.ffn2.b1, nullptr, 0.f, b.h, F, M, F, D, EPI_BIAS_SWISH)) return 1;
+  if (chain_resid_ln(c, b.att, D, w.conv.pww, w.conv.pwb, 2 * D, w.conv.pw2w, w.conv.pw2b, 1.0f, b, M, D, w.ffn2.ln, nullptr, eps)) return 1;
   LNW none{nullptr, nullptr};
-  if (gemm_resid_ln(c, b.h, F, w.ffn2.w2, w.ffn2.b2, 0.5f, b, M, D, w.ln, next_ln ? next_ln : &none, eps)) return 1;
+  if (chain_resid_ln(c, b.xn, D, w.ffn2.w1, w.ffn2.b1, F, w.ffn2.w2, w.ffn2.b2, 0.5f, b, M, D, w.ln, next_ln ? next_ln : &none, eps)) return 1;
   return 0;
 }
 
@@ -598,6 +614,7 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
     return bail(1);
   }
   if (tc_init(&h->tc) != 0) return bail(1);
+  if (const char* e = getenv("B200ASR_NO_CHAIN")) h->use_chain = !(e[0] == '1');
   *out = h;
   return 0;
 }
@@ -921,6 +938,20 @@ B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, floa
   } else {
     ENG_TRY(h, launch_attention(ap, static_cast<cudaStream_t>(stream)));
   }
+  return 0;
+}
+
+// Test hook: the chained two-GEMM kernel.  epilogue 6 or 7 as in b200asr_debug_gemm_ln; C may alias resid.
+B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const float* W1, const float* b1, const float* W2, const float* b2,
+                        const float* resid, float* C, float* C2, int M, int K1, int N1, int N2, float alpha, int epilogue,
+                        const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream) {
+  if (!h) return 1;
+  ChainGemmParams cp{};
+  cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;
+  cp.N2 = N2; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1_g; cp.ln1_b = ln1_b; cp.ln2_g = ln2_g; cp.ln2_b = ln2_b; cp.ln_eps = eps;
+  if (!tc_chain_supported(cp, epilogue)) return fail(h, "b200asr_debug_chain: shape not supported by the chained kernel");
+  h->launches++;
+  ENG_TRY(h, launch_gemm_chain(h->tc, cp, epilogue, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

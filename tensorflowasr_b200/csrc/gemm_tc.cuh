@@ -14,4 +14,17 @@ int tc_init(TcContext* ctx);
 bool tc_gemm_supported(const GemmParams& p, int epilogue);
 int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream_t stream);
 
+// Y = LN-epilogue( resid + alpha * ( swish(X . W1^T + b1) . W2^T + b2 ) )  in ONE kernel (gemm_chain.cu); the hidden
+// activations stay in TMEM.  X [M, K1] (row stride ldx), W1 [N1, K1], W2 [N2, N1], outputs C / C2 [M, N2].
+struct ChainGemmParams {
+  const float *X, *W1, *bias1, *W2, *bias2, *resid;
+  float *C, *C2;
+  int M, K1, N1, N2, ldx;
+  float alpha;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float ln_eps;
+};
+bool tc_chain_supported(const ChainGemmParams& p, int epilogue);
+int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);
+
 }  // namespace b200asr
