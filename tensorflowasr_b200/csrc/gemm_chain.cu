@@ -36,7 +36,8 @@ struct ChainParams {
 template <int EPI, int CH, int N2, int STAGES>
 __global__ void __launch_bounds__(kChainThreads, 1)
 gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
-                  const __grid_constant__ CUtensorMap map_w2, const ChainParams p) {
+                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_r,
+                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int BM = 128;
   constexpr uint32_t kXSlab = BM * 128;                               // 16 KB per 32-column slab of X
@@ -55,7 +56,8 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* act_done = acc1_full + 2;    // [2]
   uint64_t* acc2_full = act_done + 2;
   uint64_t* acc2_empty = acc2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  uint64_t* r_full = acc2_empty + 1;     // residual tile landed in the (recycled) X slabs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.n_chunks;
@@ -68,6 +70,9 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c2) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -80,6 +85,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 4);
+    mbar_init(r_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -107,15 +113,19 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       auto g2 = [&](int j) { for (int kb = 0; kb < KB2; ++kb) ring_load(&map_w2, j * CH + kb * 32, 0, N2 * 128); };
       for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
         stamp(0);
-        mbar_wait(x_empty, xphase ^ 1);                       // previous tile's first-GEMM MMAs have retired
+        mbar_wait(acc2_empty, xphase ^ 1);                    // previous tile's epilogue has left the slabs (they stage its output)
         mbar_expect_tx(x_full, (uint32_t)p.kb1 * kXSlab);
         for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d(&map_x, x_full, xs + (size_t)kb * kXSlab, kb * 32, tile * BM);
-        xphase ^= 1;
         stamp(0);
         g1(0);
         stamp(0);
         for (int j = 1; j < nch; ++j) { g1(j); stamp(0); g2(j - 1); stamp(0); }
         g2(nch - 1);
+        // the X slabs are dead once every first-GEMM MMA has retired: recycle them for the residual tile of this output
+        mbar_wait(x_empty, xphase);
+        xphase ^= 1;
+        mbar_expect_tx(r_full, (uint32_t)p.kb1 * kXSlab);
+        for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d(&map_r, r_full, xs + (size_t)kb * kXSlab, kb * 32, tile * BM);
         stamp(0);
       }
     }
@@ -190,7 +200,6 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   } else {
     // ===================================================================== activation + final epilogue (warps 2..5)
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t full_cnt[2] = {0, 0};
     uint32_t tphase = 0;
@@ -233,9 +242,8 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (warp == 2) stamp(2);
       tphase ^= 1;
       tcgen05_fence_after();
-      const int m = tile * BM + r;
-      const bool row_ok = m < p.ep.M;
-      epilogue_ln<EPI, N2>(p.ep, tmem_acc2 + lane_addr, row_ok, (size_t)m * p.ep.ldc);
+      mbar_wait(r_full, tphase ^ 1);                          // residual tile is in the slabs (tphase already flipped above)
+      epilogue_ln_tma<EPI, N2, BM>(p.ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM, quad * 32 + lane, warp == 2 && lane == 0);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
@@ -257,8 +265,8 @@ size_t chain_smem(int kb1) {
 }
 
 template <int EPI, int CH, int N2, int STAGES>
-int launch_chain_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& m2, const ChainParams& cp,
-                   cudaStream_t stream) {
+int launch_chain_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mr,
+                   const CUtensorMap& mc, const CUtensorMap& mc2, const ChainParams& cp, cudaStream_t stream) {
   auto kern = gemm_chain_kernel<EPI, CH, N2, STAGES>;
   const size_t smem = chain_smem<CH, N2, STAGES>(cp.kb1);
   static size_t configured = 0;
@@ -277,7 +285,7 @@ int launch_chain_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1,
   ChainParams cp2 = cp;
   cp2.dbg = dbg_on ? dbg : nullptr;
   if (dbg_on) cudaMemset(dbg, 0, sizeof(long long) * 192);
-  kern<<<grid, kChainThreads, smem, stream>>>(mx, m1, m2, cp2);
+  kern<<<grid, kChainThreads, smem, stream>>>(mx, m1, m2, mr, mc, mc2, cp2);
   B200_CUDA_OK(cudaGetLastError());
   if (dbg_on) {
     long long hbuf[192];
@@ -302,8 +310,9 @@ bool tc_chain_supported(const ChainGemmParams& p, int epilogue) {
   if (p.M <= 0 || p.K1 % 4 != 0 || p.N1 % 4 != 0) return false;
   if (!p.bias1 || !p.bias2 || !p.resid || !p.C || !p.C2 || !p.ln1_g) return false;
   if ((reinterpret_cast<uintptr_t>(p.X) | reinterpret_cast<uintptr_t>(p.W1) | reinterpret_cast<uintptr_t>(p.W2)) & 15) return false;
-  if (p.N2 == 144) return p.N1 % 144 == 0 && p.K1 <= 160;
-  if (p.N2 == 256) return p.N1 % 128 == 0 && p.K1 <= 256;
+  // (the X slabs are recycled for the N2-wide residual/output tile: needs ceil(K1/32) == ceil(N2/32))
+  if (p.N2 == 144) return p.N1 % 144 == 0 && p.K1 > 128 && p.K1 <= 160;
+  if (p.N2 == 256) return p.N1 % 128 == 0 && p.K1 > 224 && p.K1 <= 256;
   return false;
 }
 
@@ -341,12 +350,22 @@ int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cu
     const cuuint32_t box[2] = {32, (cuuint32_t)p.N2};
     if (encode_map(ctx, &m2, p.W2, 2, dims, strides, box, ones)) return 1;
   }
-  if (p.N2 == 144) {
-    if (epilogue == EPI_RESID_LN) return launch_chain_t<EPI_RESID_LN, 144, 144, 6>(ctx, mx, m1, m2, cp, stream);
-    return launch_chain_t<EPI_RESID_LN2, 144, 144, 6>(ctx, mx, m1, m2, cp, stream);
+  CUtensorMap mr, mc, mc2;
+  {
+    // residual in / outputs: [M, N2] tiles of 128 rows x 32-column slabs (stores clip the M and column tails)
+    const cuuint64_t dims[2] = {(cuuint64_t)p.N2, (cuuint64_t)p.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.N2 * 4};
+    const cuuint32_t box[2] = {32, 128};
+    if (encode_map(ctx, &mr, p.resid, 2, dims, strides, box, ones)) return 1;
+    if (encode_map(ctx, &mc, p.C, 2, dims, strides, box, ones)) return 1;
+    if (encode_map(ctx, &mc2, p.C2, 2, dims, strides, box, ones)) return 1;
   }
-  if (epilogue == EPI_RESID_LN) return launch_chain_t<EPI_RESID_LN, 128, 256, 2>(ctx, mx, m1, m2, cp, stream);
-  return launch_chain_t<EPI_RESID_LN2, 128, 256, 2>(ctx, mx, m1, m2, cp, stream);
+  if (p.N2 == 144) {
+    if (epilogue == EPI_RESID_LN) return launch_chain_t<EPI_RESID_LN, 144, 144, 6>(ctx, mx, m1, m2, mr, mc, mc2, cp, stream);
+    return launch_chain_t<EPI_RESID_LN2, 144, 144, 6>(ctx, mx, m1, m2, mr, mc, mc2, cp, stream);
+  }
+  if (epilogue == EPI_RESID_LN) return launch_chain_t<EPI_RESID_LN, 128, 256, 2>(ctx, mx, m1, m2, mr, mc, mc2, cp, stream);
+  return launch_chain_t<EPI_RESID_LN2, 128, 256, 2>(ctx, mx, m1, m2, mr, mc, mc2, cp, stream);
 }
 
 }  // namespace b200asr

@@ -18,26 +18,47 @@
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
 
+#include <cstring>
+
 namespace b200asr {
 
 using namespace tc;
 
 namespace {
 
+// pipeline depth: 4 stages, fewer when the LayerNorm epilogues' staging tile (BLOCK_M x BLOCK_N fp32) would not fit
+__host__ __device__ constexpr int stages_for(bool is_ln, int bn, int bm) {
+  if (!is_ln) return 4;
+  const int tile = bm * ((bn + 31) / 32) * 128;
+  for (int s = 4; s >= 2; --s)
+    if (s * (bm + bn) * 128 + tile <= 220 * 1024) return s;
+  return 2;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 template <int EPI, int BLOCK_N, int BLOCK_M>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c,
+               const __grid_constant__ CUtensorMap map_c2, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 4;     // 16 KB
   constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 4;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;     // multiple of 1024 (BLOCK_N multiple of 8)
+  constexpr bool kIsLN = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2 || EPI == EPI_BIAS_LN);
+  constexpr bool kHasResidTile = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
+  constexpr int kStages = stages_for(kIsLN, BLOCK_N, BLOCK_M);
+  constexpr int kNSlab = (BLOCK_N + 31) / 32;
+  constexpr uint32_t kStageTile = kIsLN ? (uint32_t)BLOCK_M * kNSlab * 128 : 0;   // LN epilogues: residual-in / output staging tile
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* stile = smem + kStages * kStageBytes;          // (LN epilogues) [BLOCK_M rows x kNSlab slabs of 32 columns], SW128
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stile + kStageTile);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* r_full = tmem_empty + 2;      // residual tile landed in `stile`
+  uint64_t* r_empty = r_full + 1;         // epilogue is done with `stile`
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -45,6 +66,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (kIsLN) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c2) : "memory");
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -53,6 +79,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);
     }
+    mbar_init(r_full, 1);
+    mbar_init(r_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -71,10 +99,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, rphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
         const int n0 = nt * BLOCK_N;
+        if (kHasResidTile) {   // residual tile -> staging (free once the previous tile's epilogue has stored its outputs)
+          mbar_wait(r_empty, rphase ^ 1);
+          rphase ^= 1;
+          mbar_expect_tx(r_full, kStageTile);
+          for (int sl = 0; sl < kNSlab; ++sl) tma_load_2d(&map_r, r_full, stile + (size_t)sl * BLOCK_M * 128, 32 * sl, mt * BLOCK_M);
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -130,8 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     // accumulator row held by this thread: M=128 fills all 128 lanes; M=64 uses lanes 0..15 of each quadrant
     // (cute tmem_frg: (16,4) x N with lane strides (1,32))
-    const int r = (BLOCK_M == 128) ? quad * 32 + lane : quad * 16 + (lane & 15);
-    const bool lane_ok = (BLOCK_M == 128) || lane < 16;
+    float* wsm = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * kWsmFloats;   // warp-private transpose scratch
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -139,39 +172,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      bool row_ok;
-      size_t row_off;
+      // rows of this warp: consecutive output rows starting at grow0; nrows of them are real
+      size_t grow0;
+      int nrows;
+      constexpr int kWarpRows = (BLOCK_M == 128) ? 32 : 16;
       if (p.a_mode == 0) {
-        const int m = mt * BLOCK_M + r;
-        row_ok = lane_ok && m < p.M;
-        row_off = (size_t)m * p.ldc;
+        const int m0 = mt * BLOCK_M + quad * kWarpRows;
+        grow0 = (size_t)m0;
+        nrows = min(kWarpRows, p.M - m0);
       } else {
+        // conv2: tile row r = i * F2 + f2 <-> output row ((b*T2 + tb*bt + i) * F2 + f2): consecutive; rows beyond bt / T2 clipped
         const int b = mt / p.tiles_per_b, tb = mt - b * p.tiles_per_b;
-        const int i = r / p.F2, f2 = r - i * p.F2;
-        const int t2 = tb * p.bt + i;
-        row_ok = lane_ok && (i < p.bt) && (t2 < p.T2);
-        row_off = (((size_t)b * p.T2 + t2) * p.F2 + f2) * p.ldc;
+        const int valid = min(p.bt, p.T2 - tb * p.bt) * p.F2;
+        grow0 = ((size_t)b * p.T2 + (size_t)tb * p.bt) * p.F2 + quad * 32;
+        nrows = min(32, valid - quad * 32);
       }
+      if (nrows < 0) nrows = 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      if constexpr (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2 || EPI == EPI_BIAS_LN) {
-        epilogue_ln<EPI, BLOCK_N>(p, taddr, row_ok, row_off);
+      if constexpr (kIsLN) {
+        if (kHasResidTile) mbar_wait(r_full, local & 1);
+        const int trow = (BLOCK_M == 128) ? quad * 32 + lane : (lane < 16 ? quad * 16 + lane : -1);
+        epilogue_ln_tma<EPI, BLOCK_N, BLOCK_M>(p, taddr, stile, &map_c, &map_c2, mt * BLOCK_M, trow, warp == 2 && lane == 0);
+        __syncwarp();
+        if (kHasResidTile && lane == 0) mbar_arrive(r_empty);
       } else {
-        constexpr int G = (BLOCK_N % 48 == 0) ? 48 : ((BLOCK_N % 32 == 0) ? 32 : 16);
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += G) {
-          uint32_t raw[G];
-#pragma unroll
-          for (int j = 0; j < G / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c + 16 * j), raw + 16 * j);   // warp-collective
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < G / 16; ++j) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[16 * j + i]);
-            const int n = nt * BLOCK_N + c + 16 * j;
-            if (row_ok && n < p.N) epilogue_store16<EPI>(p, v, row_off, n);
-          }
-        }
+        epilogue_plain<EPI, BLOCK_N>(p, taddr, wsm, grow0, nrows, nt * BLOCK_N, lane);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -188,38 +213,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int BLOCK_N, int BLOCK_M>
+template <int EPI, int BLOCK_N, int BLOCK_M>
 constexpr size_t smem_bytes() {
-  return (size_t)kStages * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4) + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr bool is_ln = (EPI >= EPI_RESID_LN);
+  return (size_t)stages_for(is_ln, BLOCK_N, BLOCK_M) * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4) +
+         (is_ln ? (size_t)BLOCK_M * ((BLOCK_N + 31) / 32) * 128 : (size_t)4 * kWsmFloats * 4 /*epilogue transpose scratch*/) +
+         1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 template <int EPI, int BLOCK_N, int BLOCK_M>
-int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
+int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* lnmaps, const TcParams& tp,
+               cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_tc_kernel<EPI, BLOCK_N, BLOCK_M>;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BLOCK_N, BLOCK_M>()));
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<EPI, BLOCK_N, BLOCK_M>()));
     configured = true;
   }
   const int tiles = tp.num_m_tiles * tp.num_n_tiles;
   const int grid = tiles < ctx.num_sms ? tiles : ctx.num_sms;
-  kern<<<grid, kThreads, smem_bytes<BLOCK_N, BLOCK_M>(), stream>>>(ma, mb, tp);
+  kern<<<grid, kThreads, smem_bytes<EPI, BLOCK_N, BLOCK_M>(), stream>>>(ma, mb, lnmaps[0], lnmaps[1], lnmaps[2], tp);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <int BLOCK_N, int BLOCK_M>
-int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t s) {
+int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* lnmaps, const TcParams& tp,
+                 cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS: return launch_one<EPI_BIAS, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_BIAS_RELU: return launch_one<EPI_BIAS_RELU, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_BIAS_SWISH: return launch_one<EPI_BIAS_SWISH, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_GLU: return launch_one<EPI_GLU, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_RESID: return launch_one<EPI_RESID, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_NONE: return launch_one<EPI_NONE, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_RESID_LN: return launch_one<EPI_RESID_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_RESID_LN2: return launch_one<EPI_RESID_LN2, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
-    case EPI_BIAS_LN: return launch_one<EPI_BIAS_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, tp, s);
+    case EPI_BIAS: return launch_one<EPI_BIAS, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_BIAS_RELU: return launch_one<EPI_BIAS_RELU, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_BIAS_SWISH: return launch_one<EPI_BIAS_SWISH, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_GLU: return launch_one<EPI_GLU, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_RESID: return launch_one<EPI_RESID, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_NONE: return launch_one<EPI_NONE, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_RESID_LN: return launch_one<EPI_RESID_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_RESID_LN2: return launch_one<EPI_RESID_LN2, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_BIAS_LN: return launch_one<EPI_BIAS_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
   }
   snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: bad epilogue %d", epi);
   return 1;
@@ -320,21 +350,32 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     const cuuint32_t estr[4] = {1, 2, 2, 1};
     if (encode_map(ctx, &ma, p.A, 4, dims, strides, box, estr)) return 1;
   }
+  // LayerNorm epilogues: residual-in / output tiles travel by TMA ([M, N] in BLOCK_M x 32-column slabs; stores clip tails)
+  CUtensorMap lnmaps[3];
+  memset(lnmaps, 0, sizeof(lnmaps));
+  if (epilogue >= EPI_RESID_LN) {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.ldc * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)bm};
+    if (p.resid && encode_map(ctx, &lnmaps[0], p.resid, 2, dims, strides, box, ones)) return 1;
+    if (encode_map(ctx, &lnmaps[1], p.C, 2, dims, strides, box, ones)) return 1;
+    if (encode_map(ctx, &lnmaps[2], p.C2, 2, dims, strides, box, ones)) return 1;
+  }
   if (bm == 64) {
     switch (bn) {
-      case 64: return dispatch_epi<64, 64>(ctx, epilogue, ma, mb, tp, stream);
-      case 128: return dispatch_epi<128, 64>(ctx, epilogue, ma, mb, tp, stream);
-      case 144: return dispatch_epi<144, 64>(ctx, epilogue, ma, mb, tp, stream);
-      case 192: return dispatch_epi<192, 64>(ctx, epilogue, ma, mb, tp, stream);
-      default: return dispatch_epi<256, 64>(ctx, epilogue, ma, mb, tp, stream);
+      case 64: return dispatch_epi<64, 64>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+      case 128: return dispatch_epi<128, 64>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+      case 144: return dispatch_epi<144, 64>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+      case 192: return dispatch_epi<192, 64>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+      default: return dispatch_epi<256, 64>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
     }
   }
   switch (bn) {
-    case 64: return dispatch_epi<64, 128>(ctx, epilogue, ma, mb, tp, stream);
-    case 128: return dispatch_epi<128, 128>(ctx, epilogue, ma, mb, tp, stream);
-    case 144: return dispatch_epi<144, 128>(ctx, epilogue, ma, mb, tp, stream);
-    case 192: return dispatch_epi<192, 128>(ctx, epilogue, ma, mb, tp, stream);
-    default: return dispatch_epi<256, 128>(ctx, epilogue, ma, mb, tp, stream);
+    case 64: return dispatch_epi<64, 128>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+    case 128: return dispatch_epi<128, 128>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+    case 144: return dispatch_epi<144, 128>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+    case 192: return dispatch_epi<192, 128>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
+    default: return dispatch_epi<256, 128>(ctx, epilogue, ma, mb, lnmaps, tp, stream);
   }
 }
 

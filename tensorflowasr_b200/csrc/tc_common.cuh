@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <type_traits>
+
 namespace b200asr {
 namespace tc {
 
@@ -154,168 +156,365 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue
-template <int EPI>
-__device__ __forceinline__ void epilogue_store16(const TcParams& p, float* v, size_t row_off, int n) {
-  // v: 16 consecutive accumulator columns starting at output column n of the row at C + row_off
-  if (EPI != EPI_NONE && p.bias != nullptr) {
+// In the TMEM accumulator layout a thread owns one output ROW, so naive global loads/stores touch 32 different cache lines
+// per warp instruction (measured: the LSU wavefront rate, not HBM or math, bounded every epilogue).  All global traffic of
+// the epilogues therefore goes through a warp-private shared-memory transpose: a 32-row x W-column tile is exchanged so that
+// each warp instruction moves whole 128-byte (W=32) / 64-byte (W=16) row segments.
+constexpr int kWsmLd = 36;                       // floats per row of the per-warp scratch tile (16-byte aligned, conflict-free)
+constexpr int kWsmFloats = 32 * kWsmLd;          // per warp
+
+// v[0..W) = W consecutive columns of this lane's row  ->  global rows grow0.. (coalesced).  nrows/ncols clip the tile.
+template <int W>
+__device__ __forceinline__ void warp_tile_store(float* wsm, const float* v, float* gtile, size_t ld, int nrows, int ncols, int lane) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (n + 4 * q < p.N) {
-        const float4 b = *reinterpret_cast<const float4*>(p.bias + n + 4 * q);
-        v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-      }
-    }
+  for (int q = 0; q < W / 4; ++q) *reinterpret_cast<float4*>(wsm + lane * kWsmLd + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  constexpr int CH = W / 4, RPI = 32 / CH;
+  const int q = lane % CH;
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + lane / CH;
+    if (r < nrows && 4 * q < ncols) *reinterpret_cast<float4*>(gtile + (size_t)r * ld + 4 * q) = *reinterpret_cast<const float4*>(wsm + r * kWsmLd + 4 * q);
   }
-  if (EPI == EPI_GLU) {
-    float* dst = p.C + row_off + (n >> 1);
+  __syncwarp();
+}
+template <int W>
+__device__ __forceinline__ void warp_tile_load(float* wsm, float* v, const float* gtile, size_t ld, int nrows, int ncols, int lane) {
+  constexpr int CH = W / 4, RPI = 32 / CH;
+  const int q = lane % CH;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (n + 8 * q < p.N) {
-        float4 o;
-        o.x = v[8 * q + 0] * sigmoid_fast(v[8 * q + 1]);
-        o.y = v[8 * q + 2] * sigmoid_fast(v[8 * q + 3]);
-        o.z = v[8 * q + 4] * sigmoid_fast(v[8 * q + 5]);
-        o.w = v[8 * q + 6] * sigmoid_fast(v[8 * q + 7]);
-        *reinterpret_cast<float4*>(dst + 4 * q) = o;
-      }
-    }
-    return;
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + lane / CH;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nrows && 4 * q < ncols) t = *reinterpret_cast<const float4*>(gtile + (size_t)r * ld + 4 * q);
+    *reinterpret_cast<float4*>(wsm + r * kWsmLd + 4 * q) = t;
   }
-  float* dst = p.C + row_off + n;
+  __syncwarp();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (n + 4 * q < p.N) {
-      float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      if (EPI == EPI_BIAS_RELU) {
-        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-      } else if (EPI == EPI_BIAS_SWISH) {
-        o.x = swish_fast(o.x); o.y = swish_fast(o.y); o.z = swish_fast(o.z); o.w = swish_fast(o.w);
-      } else if (EPI == EPI_RESID) {
-        const float4 r = *reinterpret_cast<const float4*>(p.resid + row_off + n + 4 * q);
-        o.x = r.x + p.alpha * o.x; o.y = r.y + p.alpha * o.y; o.z = r.z + p.alpha * o.z; o.w = r.w + p.alpha * o.w;
-      }
-      *reinterpret_cast<float4*>(dst + 4 * q) = o;
+  for (int qq = 0; qq < W / 4; ++qq) {
+    const float4 t = *reinterpret_cast<const float4*>(wsm + lane * kWsmLd + 4 * qq);
+    v[4 * qq] = t.x; v[4 * qq + 1] = t.y; v[4 * qq + 2] = t.z; v[4 * qq + 3] = t.w;
+  }
+  __syncwarp();
+}
+
+// Plain epilogues (bias / ReLU / swish / GLU / residual / none) over W accumulator columns starting at tile column c.
+//   taddr: TMEM address of this warp's lanes, column 0 of the accumulator; gcol0: global column of tile column 0
+//   grow0: global output row of lane 0; nrows: valid rows of this warp (0..32)
+template <int EPI, int W>
+__device__ __forceinline__ void epilogue_plain_group(const TcParams& p, uint32_t taddr, float* wsm, size_t grow0, int nrows, int gcol,
+                                                     int c, int lane) {
+  uint32_t raw[W];
+#pragma unroll
+  for (int j = 0; j < W / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c + 16 * j), raw + 16 * j);   // warp-collective
+  float r[W];
+  if (EPI == EPI_RESID) warp_tile_load<W>(wsm, r, p.resid + grow0 * p.ldc + gcol, p.ldc, nrows, p.N - gcol, lane);
+  tmem_ld_wait();
+  float v[W];
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI != EPI_NONE && p.bias != nullptr && gcol + 4 * q < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + 4 * q));
+    v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+    v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+  }
+  if constexpr (EPI == EPI_GLU) {
+    float o[W / 2];
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) o[i] = v[2 * i] * sigmoid_fast(v[2 * i + 1]);
+    warp_tile_store<W / 2>(wsm, o, p.C + grow0 * p.ldc + (gcol >> 1), p.ldc, nrows, (p.N - gcol) >> 1, lane);
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (EPI == EPI_BIAS_RELU) v[i] = fmaxf(v[i], 0.f);
+      else if (EPI == EPI_BIAS_SWISH) v[i] = swish_fast(v[i]);
+      else if (EPI == EPI_RESID) v[i] = r[i] + p.alpha * v[i];
     }
+    warp_tile_store<W>(wsm, v, p.C + grow0 * p.ldc + gcol, p.ldc, nrows, p.N - gcol, lane);
   }
 }
 
+template <int EPI, int BLOCK_N>
+__device__ __forceinline__ void epilogue_plain(const TcParams& p, uint32_t taddr, float* wsm, size_t grow0, int nrows, int gcol0, int lane) {
+  constexpr int FULL = (BLOCK_N / 32) * 32;
+#pragma unroll 1
+  for (int c = 0; c < FULL; c += 32) {
+    if (gcol0 + c < p.N) epilogue_plain_group<EPI, 32>(p, taddr, wsm, grow0, nrows, gcol0 + c, c, lane);   // warp-uniform
+  }
+  if (BLOCK_N % 32 != 0) {
+    if (gcol0 + FULL < p.N) epilogue_plain_group<EPI, 16>(p, taddr, wsm, grow0, nrows, gcol0 + FULL, FULL, lane);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ fused LayerNorm epilogues
 // thread == output row and BLOCK_N == N, so a row's statistics never leave the thread: the accumulator row is swept from
 // TMEM two (three) times -- statistics (shifted one-pass variance), then normalise -- instead of being parked in registers.
 template <int EPI, int BLOCK_N>
-__device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, bool row_ok, size_t row_off) {
+__device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, float* wsm, size_t grow0, int nrows, int lane_row,
+                                            int lane) {
   constexpr bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
-  constexpr int G = (BLOCK_N % 48 == 0) ? 48 : ((BLOCK_N % 32 == 0) ? 32 : 16);   // columns per batch of loads
-  // x[c0 .. c0+G) of this thread's row: accumulator (TMEM) + bias (+ residual).  All G/16 tcgen05.ld and all residual
-  // loads are issued before the first use so their latencies overlap (one exposed L2 round trip per batch, not per chunk).
-  auto load_x = [&](int c0, float* v) {
-    uint32_t raw[G];
+  const bool row_ok = lane_row < nrows;
+  float* Cw = p.C + grow0 * p.ldc;      // this warp's first row in C / C2 / resid
+  float* C2w = p.C2 + grow0 * p.ldc;
+  const float* Rw = has_resid ? p.resid + grow0 * p.ldc : nullptr;
+  // x[c .. c+W) of this thread's row = accumulator + bias (+ residual)
+  auto load_x = [&](auto wtag, int c, float* v) {
+    constexpr int W = decltype(wtag)::value;
+    uint32_t raw[W];
 #pragma unroll
-    for (int j = 0; j < G / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16 * j), raw + 16 * j);   // warp-collective
-    float4 rr[G / 4];
-    if (has_resid && row_ok) {
-#pragma unroll
-      for (int q = 0; q < G / 4; ++q) rr[q] = *reinterpret_cast<const float4*>(p.resid + row_off + c0 + 4 * q);
-    }
+    for (int j = 0; j < W / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c + 16 * j), raw + 16 * j);   // warp-collective
+    float r[W];
+    if (has_resid) warp_tile_load<W>(wsm, r, Rw + c, p.ldc, nrows, W, lane);
     tmem_ld_wait();
-    if (!row_ok) return;
 #pragma unroll
-    for (int q = 0; q < G / 4; ++q) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4 * q));
       float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
       float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
       if (has_resid) {
-        a0 = rr[q].x + p.alpha * a0; a1 = rr[q].y + p.alpha * a1; a2 = rr[q].z + p.alpha * a2; a3 = rr[q].w + p.alpha * a3;
+        a0 = r[4 * q] + p.alpha * a0; a1 = r[4 * q + 1] + p.alpha * a1; a2 = r[4 * q + 2] + p.alpha * a2; a3 = r[4 * q + 3] + p.alpha * a3;
       }
       v[4 * q + 0] = a0; v[4 * q + 1] = a1; v[4 * q + 2] = a2; v[4 * q + 3] = a3;
     }
   };
-  // re-read this thread's own row from C (written earlier by this same thread): needed because C may alias resid
-  auto load_c = [&](int c0, float* v) {
+  auto affine = [&](auto wtag, float* v, float mean, float rstd, const float* g, const float* be, int c) {
+    constexpr int W = decltype(wtag)::value;
 #pragma unroll
-    for (int q = 0; q < G / 4; ++q) {
-      const float4 r = *reinterpret_cast<const float4*>(p.C + row_off + c0 + 4 * q);
-      v[4 * q + 0] = r.x; v[4 * q + 1] = r.y; v[4 * q + 2] = r.z; v[4 * q + 3] = r.w;
-    }
-  };
-  auto store_g = [&](float* dst, const float* v) {
-#pragma unroll
-    for (int q = 0; q < G / 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  };
-  auto affine_g = [&](float* v, float mean, float rstd, const float* g, const float* be, int c0) {
-#pragma unroll
-    for (int q = 0; q < G / 4; ++q) {
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c0 + 4 * q));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c0 + 4 * q));
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c + 4 * q));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c + 4 * q));
       v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
       v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
     }
   };
+  using W32 = std::integral_constant<int, 32>;
+  using W16 = std::integral_constant<int, 16>;
+  constexpr int FULL = (BLOCK_N / 32) * 32;
+  constexpr bool TAIL = (BLOCK_N % 32) != 0;
   const float invn = 1.0f / (float)BLOCK_N;
-  // sweep 1: x (stored for *_LN modes where C holds the un-normalised stream) + statistics (shifted one-pass variance)
+
+  // sweep 1: x (stored when C keeps the un-normalised stream) + statistics (shifted one-pass variance)
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += G) {
-    float v[G];
-    load_x(c, v);
-    if (row_ok) {
-      if (c == 0) shift = v[0];
+  auto sweep1 = [&](auto wtag, int c) {
+    constexpr int W = decltype(wtag)::value;
+    float v[W];
+    load_x(wtag, c, v);
+    if (c == 0) shift = v[0];
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const float d = v[i] - shift;
-        s1 += d;
-        s2 = fmaf(d, d, s2);
-      }
-      if (EPI != EPI_RESID_LN2) store_g(p.C + row_off + c, v);
+    for (int i = 0; i < W; ++i) {
+      const float d = v[i] - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
     }
-  }
+    if (EPI != EPI_RESID_LN2) warp_tile_store<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);
+  };
+#pragma unroll 1
+  for (int c = 0; c < FULL; c += 32) sweep1(W32{}, c);
+  if (TAIL) sweep1(W16{}, FULL);
   const float m1 = s1 * invn;
   const float mean1 = shift + m1;
-  const float rstd1 = 1.0f / sqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
+  const float rstd1 = rsqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
   if (EPI != EPI_RESID_LN2) {
-    // sweep 2: LN(x; ln1) -> C2   (x read back from C: the residual operand may have been overwritten in place)
-    if (!row_ok) return;
+    // sweep 2: LN(x; ln1) -> C2   (x read back from C, coalesced: the residual operand may have been overwritten in place)
+    auto sweep2 = [&](auto wtag, int c) {
+      constexpr int W = decltype(wtag)::value;
+      float v[W];
+      warp_tile_load<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);
+      affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
+      warp_tile_store<W>(wsm, v, C2w + c, p.ldc, nrows, W, lane);
+    };
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += G) {
-      float v[G];
-      load_c(c, v);
-      affine_g(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
-      store_g(p.C2 + row_off + c, v);
-    }
+    for (int c = 0; c < FULL; c += 32) sweep2(W32{}, c);
+    if (TAIL) sweep2(W16{}, FULL);
     return;
   }
   // EPI_RESID_LN2: sweep 2: y = LN(x; ln1) -> C, statistics of y; sweep 3: LN(y; ln2) -> C2
   float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += G) {
-    float v[G];
-    load_x(c, v);
-    if (row_ok) {
-      affine_g(v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
-      if (c == 0) shift2 = v[0];
+  auto sweep2b = [&](auto wtag, int c) {
+    constexpr int W = decltype(wtag)::value;
+    float v[W];
+    load_x(wtag, c, v);
+    affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
+    if (c == 0) shift2 = v[0];
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const float d = v[i] - shift2;
-        t1 += d;
-        t2 = fmaf(d, d, t2);
-      }
-      store_g(p.C + row_off + c, v);
+    for (int i = 0; i < W; ++i) {
+      const float d = v[i] - shift2;
+      t1 += d;
+      t2 = fmaf(d, d, t2);
     }
-  }
-  if (p.ln2_g == nullptr || !row_ok) return;
+    warp_tile_store<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);
+  };
+#pragma unroll 1
+  for (int c = 0; c < FULL; c += 32) sweep2b(W32{}, c);
+  if (TAIL) sweep2b(W16{}, FULL);
+  if (p.ln2_g == nullptr) return;
   const float m2 = t1 * invn;
   const float mean2 = shift2 + m2;
-  const float rstd2 = 1.0f / sqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
+  const float rstd2 = rsqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
+  auto sweep3 = [&](auto wtag, int c) {
+    constexpr int W = decltype(wtag)::value;
+    float v[W];
+    warp_tile_load<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);     // y, as stored in sweep 2
+    affine(wtag, v, mean2, rstd2, p.ln2_g, p.ln2_b, c);
+    warp_tile_store<W>(wsm, v, C2w + c, p.ldc, nrows, W, lane);
+  };
 #pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += G) {
-    float v[G];
-    load_c(c, v);                     // y, as stored in sweep 2
-    affine_g(v, mean2, rstd2, p.ln2_g, p.ln2_b, c);
-    store_g(p.C2 + row_off + c, v);
-  }
+  for (int c = 0; c < FULL; c += 32) sweep3(W32{}, c);
+  if (TAIL) sweep3(W16{}, FULL);
+  (void)row_ok;
 }
 
+// ------------------------------------------------------------------------------------------------ LayerNorm epilogue through a TMA-staged tile
+// The residual tile is fetched by TMA into shared memory while the MMAs run; the epilogue works on it in place (thread ==
+// row, SWIZZLE_128B slabs of 32 columns: conflict-free 16-byte accesses) and the results leave through TMA stores.  No
+// global-memory latency is exposed to the epilogue warps and every global transaction is a full line.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int EPI, int BLOCK_N, int ROWS>
+__device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t taddr, uint8_t* stile, const CUtensorMap* map_c,
+                                                const CUtensorMap* map_c2, int row0, int trow, bool issuer) {
+  constexpr bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
+  constexpr int NSLAB = (BLOCK_N + 31) / 32;
+  const bool active = trow >= 0;
+  auto chunk_ptr = [&](int s, int q) -> float4* {   // 16-byte chunk q (4 columns) of slab s in this thread's row
+    return reinterpret_cast<float4*>(stile + (size_t)s * ROWS * 128 + (size_t)(active ? trow : 0) * 128 + (((q ^ (trow & 7)) & 7) << 4));
+  };
+  auto store_tile = [&](const CUtensorMap* map) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    epi_bar_sync();
+    if (issuer) {
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) tma_store_2d(map, stile + (size_t)s * ROWS * 128, 32 * s, row0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    epi_bar_sync();   // the tile may be overwritten again
+  };
+  // x = acc + bias (+ resid from smem) for the W columns of slab s
+  auto load_x = [&](auto wtag, int s, float* v) {
+    constexpr int W = decltype(wtag)::value;
+    uint32_t raw[W];
+#pragma unroll
+    for (int j = 0; j < W / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(32 * s + 16 * j), raw + 16 * j);   // warp-collective
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + 32 * s + 4 * q));
+      float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
+      float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
+      if (has_resid) {
+        const float4 r = *chunk_ptr(s, q);
+        a0 = r.x + p.alpha * a0; a1 = r.y + p.alpha * a1; a2 = r.z + p.alpha * a2; a3 = r.w + p.alpha * a3;
+      }
+      v[4 * q + 0] = a0; v[4 * q + 1] = a1; v[4 * q + 2] = a2; v[4 * q + 3] = a3;
+    }
+  };
+  auto put = [&](auto wtag, int s, const float* v) {
+    constexpr int W = decltype(wtag)::value;
+    if (!active) return;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) *chunk_ptr(s, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  };
+  auto get = [&](auto wtag, int s, float* v) {
+    constexpr int W = decltype(wtag)::value;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 t = *chunk_ptr(s, q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  };
+  auto affine = [&](auto wtag, float* v, float mean, float rstd, const float* g, const float* be, int s) {
+    constexpr int W = decltype(wtag)::value;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + 32 * s + 4 * q));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + 32 * s + 4 * q));
+      v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
+      v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
+    }
+  };
+  using W32 = std::integral_constant<int, 32>;
+  using W16 = std::integral_constant<int, 16>;
+  constexpr int NFULL = BLOCK_N / 32;
+  constexpr bool TAIL = (BLOCK_N % 32) != 0;
+  const float invn = 1.0f / (float)BLOCK_N;
+
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+  auto sweep1 = [&](auto wtag, int s) {
+    constexpr int W = decltype(wtag)::value;
+    float v[W];
+    load_x(wtag, s, v);
+    if (s == 0) shift = v[0];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float d = v[i] - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
+    if (EPI != EPI_RESID_LN2) put(wtag, s, v);
+  };
+#pragma unroll 1
+  for (int s = 0; s < NFULL; ++s) sweep1(W32{}, s);
+  if (TAIL) sweep1(W16{}, NFULL);
+  const float m1 = s1 * invn;
+  const float mean1 = shift + m1;
+  const float rstd1 = rsqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
+
+  if (EPI != EPI_RESID_LN2) {
+    store_tile(map_c);                                   // C = x
+    auto sweep2 = [&](auto wtag, int s) {
+      constexpr int W = decltype(wtag)::value;
+      float v[W];
+      get(wtag, s, v);
+      affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, s);
+      put(wtag, s, v);
+    };
+#pragma unroll 1
+    for (int s = 0; s < NFULL; ++s) sweep2(W32{}, s);
+    if (TAIL) sweep2(W16{}, NFULL);
+    store_tile(map_c2);                                  // C2 = LN(x; ln1)
+    return;
+  }
+  float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
+  auto sweep2b = [&](auto wtag, int s) {
+    constexpr int W = decltype(wtag)::value;
+    float v[W];
+    load_x(wtag, s, v);
+    affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, s);
+    if (s == 0) shift2 = v[0];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float d = v[i] - shift2;
+      t1 += d;
+      t2 = fmaf(d, d, t2);
+    }
+    put(wtag, s, v);
+  };
+#pragma unroll 1
+  for (int s = 0; s < NFULL; ++s) sweep2b(W32{}, s);
+  if (TAIL) sweep2b(W16{}, NFULL);
+  store_tile(map_c);                                     // C = y = LN(x; ln1)
+  if (p.ln2_g == nullptr) return;
+  const float m2 = t1 * invn;
+  const float mean2 = shift2 + m2;
+  const float rstd2 = rsqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
+  auto sweep3 = [&](auto wtag, int s) {
+    constexpr int W = decltype(wtag)::value;
+    float v[W];
+    get(wtag, s, v);
+    affine(wtag, v, mean2, rstd2, p.ln2_g, p.ln2_b, s);
+    put(wtag, s, v);
+  };
+#pragma unroll 1
+  for (int s = 0; s < NFULL; ++s) sweep3(W32{}, s);
+  if (TAIL) sweep3(W16{}, NFULL);
+  store_tile(map_c2);                                    // C2 = LN(y; ln2)
+}
 
 // ------------------------------------------------------------------------------------------------ host side
 using EncodeTiledFn = PFN_cuTensorMapEncodeTiled_v12000;
