@@ -15,6 +15,8 @@
 // An optional band (chunk_conformer_blocks.py:158-176) restricts the visible keys per query.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace b200asr {
 
 namespace {
@@ -26,11 +28,8 @@ constexpr int kThreadsA = 384;     // warps 0-3: softmax rows (thread == query),
 constexpr unsigned kSpin = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float to_tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round-to-nearest (ties away) to tf32 on the integer ALU
+__device__ __forceinline__ float to_tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void mbar_init_a(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32a(bar)), "r"(count));
 }
@@ -127,6 +126,11 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y;
+  int ev = 0;
+  auto stamp = [&]() {
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && ev < 64) p.dbg[ev++] = clock64();
+  };
+  stamp();
   const int dh = p.dh, ld = 3 * p.H * dh;
   const float* base = p.qkv + (size_t)b * p.T * ld;
   const float* qbase = base + h * dh;
@@ -202,7 +206,9 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   };
 
   for (int q0 = blockIdx.x * kQT; q0 < p.T; q0 += gridDim.x * kQT) {
+  stamp();
   stage_rows(Qs, qbase, q0, kQT);               // rows beyond T and columns beyond dh are zero
+  stamp();
 
   // per-row state (threads 0..127: thread == query row)
   const int qi = q0 + tid;
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
       stage_vt(k0);
       kv_loaded = true;
     }
+    stamp();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
     fence_before();
     __syncthreads();
@@ -242,6 +249,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
       __syncwarp();
     }
     mbar_wait_a(mma_bar, phase);
+    stamp();
     phase ^= 1;
     fence_after();
     // ---- softmax over this block's keys, P written back in place
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
       l_run = l_run * corr + sum;
       m_run = m_new;
     }
+    stamp();
     fence_before();
     __syncthreads();
     // ---- O_blk = P V   (A from TMEM)
@@ -303,6 +312,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
       __syncwarp();
     }
     mbar_wait_a(mma_bar, phase);
+    stamp();
     phase ^= 1;
     fence_after();
     if (warp < 4) {
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
             make_float4(o[4 * c4] * inv, o[4 * c4 + 1] * inv, o[4 * c4 + 2] * inv, o[4 * c4 + 3] * inv);
     }
   }
+  stamp();
   }  // query tiles
   fence_before();
   __syncthreads();
@@ -355,8 +366,28 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
   // one CTA per (batch, head) when the whole sequence is a single key block (K / V^T staged once for all query tiles)
   const int qtiles = ceil_div(p.T, kQT);
   dim3 grid(p.T <= kKT ? 1 : qtiles, p.H, p.B);
-  attention_tc_kernel<<<grid, kThreadsA, smem, stream>>>(p);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("B200ASR_ATTN_DBG");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg, sizeof(long long) * 64);
+  }
+  AttnParams pp = p;
+  if (dbg_on) {
+    pp.dbg = dbg;
+    cudaMemset(dbg, 0, sizeof(long long) * 64);
+  }
+  attention_tc_kernel<<<grid, kThreadsA, smem, stream>>>(pp);
   B200_CUDA_OK(cudaGetLastError());
+  if (dbg_on) {
+    long long hb[64];
+    cudaDeviceSynchronize();
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "attn-dbg:");
+    for (int i = 0; i < 64 && hb[i]; ++i) fprintf(stderr, " %lld", hb[i] - hb[0]);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 

@@ -22,7 +22,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kChainThreads = 192;
+constexpr int kChainThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 activation / epilogue (two per TMEM lane quadrant)
 
 struct ChainParams {
   TcParams ep;          // final epilogue (bias = b2, resid, C, C2, ln params, alpha, M, N = N2, ldc)
@@ -58,6 +58,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* acc2_empty = acc2_full + 1;
   uint64_t* r_full = acc2_empty + 1;     // residual tile landed in the (recycled) X slabs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 1);
+  float* statbuf = reinterpret_cast<float*>(tmem_slot + 4);   // [128 rows][2 halves][4] LayerNorm partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.n_chunks;
@@ -81,10 +82,10 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     mbar_init(x_empty, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc1_full[a], 1);
-      mbar_init(&act_done[a], 4);
+      mbar_init(&act_done[a], 8);
     }
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 4);
+    mbar_init(acc2_empty, 8);
     mbar_init(r_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -198,9 +199,13 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       tphase ^= 1;
     }
   } else {
-    // ===================================================================== activation + final epilogue (warps 2..5)
-    const int quad = warp & 3;
+    // ===================================================================== activation + final epilogue (warps 2..9)
+    const int quad = warp & 3;                       // TMEM lane quadrant (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;                // which half of the columns this warp handles
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    constexpr int kUnits = CH / 16;
+    constexpr int kSplit = (kUnits + 1) / 2;
+    const int cu0 = half ? kSplit : 0, cu1 = half ? kUnits : kSplit;
     uint32_t full_cnt[2] = {0, 0};
     uint32_t tphase = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
@@ -212,23 +217,26 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         full_cnt[a]++;
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(a * CH);
-        constexpr int G = (CH % 48 == 0) ? 48 : 32;
-#pragma unroll 1
-        for (int c = 0; c < CH; c += G) {
-          uint32_t raw[G];
+        // all of this warp's columns are fetched from TMEM before the first use (one exposed TMEM round trip per chunk)
+        uint32_t raw[kSplit][16];
 #pragma unroll
-          for (int q = 0; q < G / 16; ++q) tmem_ld16_nowait(taddr + (uint32_t)(c + 16 * q), raw + 16 * q);
-          tmem_ld_wait();
+        for (int i = 0; i < kSplit; ++i)
+          if (cu0 + i < cu1) tmem_ld16_nowait(taddr + (uint32_t)(16 * (cu0 + i)), raw[i]);   // warp-uniform predicate
+        tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < G / 4; ++q) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias1 + j * CH + c + 4 * q));
-            raw[4 * q + 0] = tf32_rn_bits(swish_fast(__uint_as_float(raw[4 * q + 0]) + b.x));
-            raw[4 * q + 1] = tf32_rn_bits(swish_fast(__uint_as_float(raw[4 * q + 1]) + b.y));
-            raw[4 * q + 2] = tf32_rn_bits(swish_fast(__uint_as_float(raw[4 * q + 2]) + b.z));
-            raw[4 * q + 3] = tf32_rn_bits(swish_fast(__uint_as_float(raw[4 * q + 3]) + b.w));
+        for (int i = 0; i < kSplit; ++i) {
+          if (cu0 + i < cu1) {
+            const int u = cu0 + i;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias1 + j * CH + 16 * u + 4 * q));
+              raw[i][4 * q + 0] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 0]) + b.x));
+              raw[i][4 * q + 1] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 1]) + b.y));
+              raw[i][4 * q + 2] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 2]) + b.z));
+              raw[i][4 * q + 3] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 3]) + b.w));
+            }
+            tmem_st16(taddr + (uint32_t)(16 * u), raw[i]);
           }
-#pragma unroll
-          for (int q = 0; q < G / 16; ++q) tmem_st16(taddr + (uint32_t)(c + 16 * q), raw + 16 * q);
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -243,7 +251,11 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       tphase ^= 1;
       tcgen05_fence_after();
       mbar_wait(r_full, tphase ^ 1);                          // residual tile is in the slabs (tphase already flipped above)
-      epilogue_ln_tma<EPI, N2, BM>(p.ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM, quad * 32 + lane, warp == 2 && lane == 0);
+      // the weight ring is idle from here until the next tile's first load (the producer is gated on acc2_empty): use it as
+      // the second staging tile so the C store is not waited for before C2 is produced
+      constexpr bool kRingFits = (size_t)STAGES * kRing >= (size_t)BM * ((N2 + 31) / 32) * 128;
+      epilogue_ln_tma<EPI, N2, BM, 2>(p.ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM, quad * 32 + lane,
+                                      warp == 2 && lane == 0, half, statbuf, kRingFits ? ring : nullptr);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
@@ -261,7 +273,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
 template <int CH, int N2, int STAGES>
 size_t chain_smem(int kb1) {
-  return (size_t)kb1 * 128 * 128 + (size_t)STAGES * (CH > N2 ? CH : N2) * 128 + 1024 + 256;
+  return (size_t)kb1 * 128 * 128 + (size_t)STAGES * (CH > N2 ? CH : N2) * 128 + 1024 + 256 + 128 * 2 * 4 * 4 /*LayerNorm partial sums*/;
 }
 
 template <int EPI, int CH, int N2, int STAGES>

@@ -72,6 +72,7 @@ struct AttnParams {
   int B, T, H, dh;
   // optional band mask (ChunkConformer, chunk_conformer_blocks.py:158-176); win_front < 0 => full attention
   int win_front, win_back;
+  long long* dbg = nullptr;   // optional clock64 timeline of CTA 0 (B200ASR_ATTN_DBG=1)
 };
 int launch_attention(const AttnParams& p, cudaStream_t stream);          // fp32 CUDA cores (block_ops.cu)
 bool attention_tc_supported(const AttnParams& p);

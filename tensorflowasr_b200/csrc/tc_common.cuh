@@ -120,8 +120,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float swish_fast(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sigmoid(x) = 0.5 + 0.5 tanh(x/2): ONE MUFU op per element (tanh.approx, ~2^-11 relative: at the tf32 input-rounding level)
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float swish_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -140,11 +149,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t tf32_rn_bits(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa on the integer ALU (cvt.rna.tf32 sits on a slow conversion pipe)
+__device__ __forceinline__ uint32_t tf32_rn_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 // D[tmem] (+)= A[tmem] . B[smem]^T   (A: 128 lanes x K columns of tf32, B K-major)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -373,147 +379,156 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
-template <int EPI, int BLOCK_N, int ROWS>
+// HALVES == 2: two warps share each TMEM lane quadrant and split the row's columns (16-column units [u0, u1)); the LayerNorm
+// partial sums are exchanged through `statbuf` ([ROWS][2][2] floats).  With column-split statistics the variance is the
+// plain E[x^2] - mean^2 (no common shift is available); fp32 is ample for |x| <~ 1e3 over <= 256 columns.
+template <int EPI, int BLOCK_N, int ROWS, int HALVES = 1>
 __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t taddr, uint8_t* stile, const CUtensorMap* map_c,
-                                                const CUtensorMap* map_c2, int row0, int trow, bool issuer) {
+                                                const CUtensorMap* map_c2, int row0, int trow, bool issuer, int half = 0,
+                                                float* statbuf = nullptr, uint8_t* stile2 = nullptr) {
   constexpr bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
   constexpr int NSLAB = (BLOCK_N + 31) / 32;
+  constexpr int NUNIT = BLOCK_N / 16;                    // 16-column units
+  constexpr int SPLIT = (HALVES == 2) ? (NUNIT + 1) / 2 : NUNIT;
+  const int u0 = (HALVES == 2 && half == 1) ? SPLIT : 0;
+  const int u1 = (HALVES == 2 && half == 0) ? SPLIT : NUNIT;
   const bool active = trow >= 0;
-  auto chunk_ptr = [&](int s, int q) -> float4* {   // 16-byte chunk q (4 columns) of slab s in this thread's row
-    return reinterpret_cast<float4*>(stile + (size_t)s * ROWS * 128 + (size_t)(active ? trow : 0) * 128 + (((q ^ (trow & 7)) & 7) << 4));
+  auto chunk_ptr_in = [&](uint8_t* base, int u, int q) -> float4* {   // 16-byte chunk q (0..3) of unit u in this thread's row
+    const int s = u >> 1, qq = ((u & 1) << 2) | q;
+    return reinterpret_cast<float4*>(base + (size_t)s * ROWS * 128 + (size_t)(active ? trow : 0) * 128 + (((qq ^ (trow & 7)) & 7) << 4));
   };
-  auto store_tile = [&](const CUtensorMap* map) {
+  auto chunk_ptr = [&](int u, int q) -> float4* { return chunk_ptr_in(stile, u, q); };
+  uint8_t* out2 = stile2 ? stile2 : stile;              // where the second output is staged
+  // TMA-store the staged tile.  wait_read: block until the store has finished READING shared memory (tile reusable).
+  auto store_tile = [&](const CUtensorMap* map, uint8_t* base, bool wait_read) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    epi_bar_sync();
+    epi_bar_sync<128 * HALVES>();
     if (issuer) {
 #pragma unroll
-      for (int s = 0; s < NSLAB; ++s) tma_store_2d(map, stile + (size_t)s * ROWS * 128, 32 * s, row0);
+      for (int s = 0; s < NSLAB; ++s) tma_store_2d(map, base + (size_t)s * ROWS * 128, 32 * s, row0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (wait_read) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    epi_bar_sync();   // the tile may be overwritten again
+    if (wait_read) epi_bar_sync<128 * HALVES>();   // the tile(s) may be overwritten again
   };
-  // x = acc + bias (+ resid from smem) for the W columns of slab s
-  auto load_x = [&](auto wtag, int s, float* v) {
-    constexpr int W = decltype(wtag)::value;
-    uint32_t raw[W];
-#pragma unroll
-    for (int j = 0; j < W / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(32 * s + 16 * j), raw + 16 * j);   // warp-collective
+  // combine per-half partial sums (sum, sum of squares) of this row
+  auto combine = [&](float& a, float& b, int slot) {
+    if (HALVES == 1) return;
+    float* mine = statbuf + ((size_t)(active ? trow : 0) * 2 + half) * 4 + slot * 2;
+    if (active) { mine[0] = a; mine[1] = b; }
+    epi_bar_sync<128 * HALVES>();
+    const float* other = statbuf + ((size_t)(active ? trow : 0) * 2 + (half ^ 1)) * 4 + slot * 2;
+    a += other[0];
+    b += other[1];
+  };
+  // x = acc + bias (+ resid from smem) for the 16 columns of unit u
+  auto load_x = [&](int u, float* v) {
+    uint32_t raw[16];
+    tmem_ld16_nowait(taddr + (uint32_t)(16 * u), raw);   // warp-collective
     tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + 32 * s + 4 * q));
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + 16 * u + 4 * q));
       float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
       float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
       if (has_resid) {
-        const float4 r = *chunk_ptr(s, q);
+        const float4 r = *chunk_ptr(u, q);
         a0 = r.x + p.alpha * a0; a1 = r.y + p.alpha * a1; a2 = r.z + p.alpha * a2; a3 = r.w + p.alpha * a3;
       }
       v[4 * q + 0] = a0; v[4 * q + 1] = a1; v[4 * q + 2] = a2; v[4 * q + 3] = a3;
     }
   };
-  auto put = [&](auto wtag, int s, const float* v) {
-    constexpr int W = decltype(wtag)::value;
+  auto put_in = [&](uint8_t* base, int u, const float* v) {
     if (!active) return;
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) *chunk_ptr(s, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) *chunk_ptr_in(base, u, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   };
-  auto get = [&](auto wtag, int s, float* v) {
-    constexpr int W = decltype(wtag)::value;
+  auto put = [&](int u, const float* v) { put_in(stile, u, v); };
+  auto get = [&](int u, float* v) {
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-      const float4 t = *chunk_ptr(s, q);
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = *chunk_ptr(u, q);
       v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
   };
-  auto affine = [&](auto wtag, float* v, float mean, float rstd, const float* g, const float* be, int s) {
-    constexpr int W = decltype(wtag)::value;
+  auto affine = [&](float* v, float mean, float rstd, const float* g, const float* be, int u) {
 #pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + 32 * s + 4 * q));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + 32 * s + 4 * q));
+    for (int q = 0; q < 4; ++q) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + 16 * u + 4 * q));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + 16 * u + 4 * q));
       v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
       v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
     }
   };
-  using W32 = std::integral_constant<int, 32>;
-  using W16 = std::integral_constant<int, 16>;
-  constexpr int NFULL = BLOCK_N / 32;
-  constexpr bool TAIL = (BLOCK_N % 32) != 0;
   const float invn = 1.0f / (float)BLOCK_N;
 
+  // sweep 1: x (kept in the tile when C holds the un-normalised stream) + statistics
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
-  auto sweep1 = [&](auto wtag, int s) {
-    constexpr int W = decltype(wtag)::value;
-    float v[W];
-    load_x(wtag, s, v);
-    if (s == 0) shift = v[0];
+#pragma unroll 1
+  for (int u = u0; u < u1; ++u) {
+    float v[16];
+    load_x(u, v);
+    if (HALVES == 1 && u == 0) shift = v[0];              // shifted one-pass variance when one thread sees the whole row
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
+    for (int i = 0; i < 16; ++i) {
       const float d = v[i] - shift;
       s1 += d;
       s2 = fmaf(d, d, s2);
     }
-    if (EPI != EPI_RESID_LN2) put(wtag, s, v);
-  };
-#pragma unroll 1
-  for (int s = 0; s < NFULL; ++s) sweep1(W32{}, s);
-  if (TAIL) sweep1(W16{}, NFULL);
+    if (EPI != EPI_RESID_LN2) put(u, v);
+  }
+  combine(s1, s2, 0);
   const float m1 = s1 * invn;
   const float mean1 = shift + m1;
   const float rstd1 = rsqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
 
   if (EPI != EPI_RESID_LN2) {
-    store_tile(map_c);                                   // C = x
-    auto sweep2 = [&](auto wtag, int s) {
-      constexpr int W = decltype(wtag)::value;
-      float v[W];
-      get(wtag, s, v);
-      affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, s);
-      put(wtag, s, v);
-    };
+    store_tile(map_c, stile, stile2 == nullptr);         // C = x   (no wait when C2 is staged elsewhere)
 #pragma unroll 1
-    for (int s = 0; s < NFULL; ++s) sweep2(W32{}, s);
-    if (TAIL) sweep2(W16{}, NFULL);
-    store_tile(map_c2);                                  // C2 = LN(x; ln1)
+    for (int u = u0; u < u1; ++u) {
+      float v[16];
+      get(u, v);
+      affine(v, mean1, rstd1, p.ln1_g, p.ln1_b, u);
+      put_in(out2, u, v);
+    }
+    store_tile(map_c2, out2, true);                      // C2 = LN(x; ln1)
     return;
   }
   float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
-  auto sweep2b = [&](auto wtag, int s) {
-    constexpr int W = decltype(wtag)::value;
-    float v[W];
-    load_x(wtag, s, v);
-    affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, s);
-    if (s == 0) shift2 = v[0];
+#pragma unroll 1
+  for (int u = u0; u < u1; ++u) {
+    float v[16];
+    load_x(u, v);
+    affine(v, mean1, rstd1, p.ln1_g, p.ln1_b, u);
+    if (HALVES == 1 && u == 0) shift2 = v[0];
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
+    for (int i = 0; i < 16; ++i) {
       const float d = v[i] - shift2;
       t1 += d;
       t2 = fmaf(d, d, t2);
     }
-    put(wtag, s, v);
-  };
-#pragma unroll 1
-  for (int s = 0; s < NFULL; ++s) sweep2b(W32{}, s);
-  if (TAIL) sweep2b(W16{}, NFULL);
-  store_tile(map_c);                                     // C = y = LN(x; ln1)
-  if (p.ln2_g == nullptr) return;
+    put(u, v);
+  }
+  if (p.ln2_g == nullptr) {
+    store_tile(map_c, stile, true);
+    return;
+  }
+  store_tile(map_c, stile, stile2 == nullptr);           // C = y = LN(x; ln1)
+  combine(t1, t2, 1);
   const float m2 = t1 * invn;
   const float mean2 = shift2 + m2;
   const float rstd2 = rsqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
-  auto sweep3 = [&](auto wtag, int s) {
-    constexpr int W = decltype(wtag)::value;
-    float v[W];
-    get(wtag, s, v);
-    affine(wtag, v, mean2, rstd2, p.ln2_g, p.ln2_b, s);
-    put(wtag, s, v);
-  };
 #pragma unroll 1
-  for (int s = 0; s < NFULL; ++s) sweep3(W32{}, s);
-  if (TAIL) sweep3(W16{}, NFULL);
-  store_tile(map_c2);                                    // C2 = LN(y; ln2)
+  for (int u = u0; u < u1; ++u) {
+    float v[16];
+    get(u, v);
+    affine(v, mean2, rstd2, p.ln2_g, p.ln2_b, u);
+    put_in(out2, u, v);
+  }
+  store_tile(map_c2, out2, true);                        // C2 = LN(y; ln2)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
