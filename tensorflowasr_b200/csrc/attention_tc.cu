@@ -24,7 +24,9 @@ namespace {
 constexpr int kQT = 128;     // queries per CTA
 constexpr int kKT = 256;     // keys per block
 constexpr int kDP = 64;      // head dim padded to two 32-float swizzle slabs
-constexpr int kThreadsA = 384;     // warps 0-3: softmax rows (thread == query), warp 4: MMA issue + TMEM, all 12: tile staging
+constexpr int kThreadsA = 384;     // warps 0-7: softmax (two per TMEM lane quadrant, 128 key columns each), warp 8: MMA issue +
+                                   // TMEM, all 12 warps: tile staging
+constexpr int kMmaWarp = 8;
 constexpr unsigned kSpin = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   uint8_t* Vt = Ks + 2 * kKT * 128;                    // 8 slabs x  64 rows x 128 B = 64 KB   (V transposed: rows = head dim)
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(Vt + 8 * kDP * 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);      // [2 kinds][128 rows][2 halves] partial max / sum exchange
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     mbar_init_a(mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32a(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -210,14 +213,18 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   stage_rows(Qs, qbase, q0, kQT);               // rows beyond T and columns beyond dh are zero
   stamp();
 
-  // per-row state (threads 0..127: thread == query row)
-  const int qi = q0 + tid;
+  // per-row state: warps 0..7, row = (warp & 3) * 32 + lane; `half` selects this thread's 128 key columns of a block and
+  // its 32 output columns
+  const int half = (warp >> 2) & 1;
+  const int row = (warp & 3) * 32 + lane;
+  const int qi = q0 + row;
   float m_run = -INFINITY, l_run = 0.f;
-  float o[kDP];
+  float o[32];
 #pragma unroll
-  for (int d = 0; d < kDP; ++d) o[d] = 0.f;
+  for (int d = 0; d < 32; ++d) o[d] = 0.f;
   int lo = 0, hi = p.T - 1;
-  if (p.win_front >= 0) {
+  const bool band = p.win_front >= 0;
+  if (band) {
     lo = max(min(max(qi - p.win_front, 0), p.T - p.win_back), 0);
     hi = min(max(min(qi + p.win_back, p.T), p.win_back), p.T - 1);
   }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     fence_before();
     __syncthreads();
     // ---- S = Q K^T
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
       fence_after();
       if (lane == 0) {
         const uint32_t qa = smem_u32a(Qs), ka = smem_u32a(Ks);
@@ -252,56 +259,78 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     stamp();
     phase ^= 1;
     fence_after();
-    // ---- softmax over this block's keys, P written back in place
+    // ---- softmax over this block's keys (8 warps: each thread sweeps its 128 columns twice), P written back in place
     float corr = 1.f;
-    if (warp < 4) {
-      const int nk = min(kKT, p.T - k0);
+    const int nk = min(kKT, p.T - k0);
+    if (warp < 8) {
+      const int cbeg = half * (kKT / 2), cend = cbeg + kKT / 2;
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < kKT; c += 32) {
+      for (int c = cbeg; c < cend; c += 32) {
         if (c >= nk) break;                            // warp-uniform: whole chunk beyond the sequence
         uint32_t r[32];
         tmem_ld32(tmem_S + lane_addr + (uint32_t)c, r);
+        if (!band && c + 32 <= nk) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = k0 + c + j;
-          if (c + j < nk && key >= lo && key <= hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = k0 + c + j;
+            if (c + j < nk && key >= lo && key <= hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
         }
       }
+      red[row * 2 + half] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      mx = fmaxf(red[row * 2], red[row * 2 + 1]);
       const float m_new = fmaxf(m_run, mx);
       const bool any = (m_new != -INFINITY);
       corr = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
       if (!any) corr = 1.f;
+      const float mscaled = m_new * 1.4426950408889634f;
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < kKT; c += 32) {
+      for (int c = cbeg; c < cend; c += 32) {
         if (c >= ((nk + 7) & ~7)) break;               // P columns at or beyond ceil8(nk) are never read by the P.V MMAs
         uint32_t r[32];
         tmem_ld32(tmem_S + lane_addr + (uint32_t)c, r);
+        if (!band && c + 32 <= nk) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = k0 + c + j;
-          float pv = 0.f;
-          if (any && c + j < nk && key >= lo && key <= hi) pv = __expf(__uint_as_float(r[j]) - m_new);
-          const uint32_t pt = __float_as_uint(pv) & 0xFFFFE000u;   // what the tf32 datapath will see
-          sum += __uint_as_float(pt);
-          r[j] = pt;
+          for (int j = 0; j < 32; ++j) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(r[j]), 1.4426950408889634f, -mscaled)));
+            const uint32_t pt = __float_as_uint(e) & 0xFFFFE000u;   // what the tf32 datapath will see
+            sum += __uint_as_float(pt);
+            r[j] = pt;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = k0 + c + j;
+            float pv = 0.f;
+            if (any && c + j < nk && key >= lo && key <= hi) pv = __expf(__uint_as_float(r[j]) - m_new);
+            const uint32_t pt = __float_as_uint(pv) & 0xFFFFE000u;
+            sum += __uint_as_float(pt);
+            r[j] = pt;
+          }
         }
         tmem_st32(tmem_S + lane_addr + (uint32_t)c, r);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      l_run = l_run * corr + sum;
+      red[256 + row * 2 + half] = sum;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      l_run = l_run * corr + red[256 + row * 2] + red[256 + row * 2 + 1];
       m_run = m_new;
     }
     stamp();
     fence_before();
     __syncthreads();
     // ---- O_blk = P V   (A from TMEM)
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
       fence_after();
       if (lane == 0) {
         const uint32_t va = smem_u32a(Vt);
-        const int nk = min(kKT, p.T - k0);
         const int ksteps = (nk + 7) / 8;               // keys beyond nk have P == 0 and V^T == 0
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t db = smem_desc_sw128(va + (ks >> 2) * (kDP * 128) + (ks & 3) * 32);
@@ -315,26 +344,23 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     stamp();
     phase ^= 1;
     fence_after();
-    if (warp < 4) {
+    if (warp < 8) {
+      uint32_t r[32];
+      tmem_ld32(tmem_O + lane_addr + (uint32_t)(32 * half), r);
 #pragma unroll
-      for (int c = 0; c < kDP; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_O + lane_addr + (uint32_t)c, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[c + j] = o[c + j] * corr + __uint_as_float(r[j]);
-      }
+      for (int j = 0; j < 32; ++j) o[j] = o[j] * corr + __uint_as_float(r[j]);
     }
     fence_before();
     __syncthreads();   // S/P, O_blk and the Q/K/V tiles may be overwritten next
     fence_after();
   }
 
-  if (warp < 4 && qi < p.T) {
+  if (warp < 8 && qi < p.T) {
     const float inv = 1.0f / l_run;
-    float* orow = p.out + ((size_t)b * p.T + qi) * (p.H * dh) + h * dh;
+    float* orow = p.out + ((size_t)b * p.T + qi) * (p.H * dh) + h * dh + 32 * half;
 #pragma unroll
-    for (int c4 = 0; c4 < kDP / 4; ++c4) {
-      if (4 * c4 < dh)
+    for (int c4 = 0; c4 < 8; ++c4) {
+      if (32 * half + 4 * c4 < dh)
         *reinterpret_cast<float4*>(orow + 4 * c4) =
             make_float4(o[4 * c4] * inv, o[4 * c4 + 1] * inv, o[4 * c4 + 2] * inv, o[4 * c4 + 3] * inv);
     }
@@ -343,7 +369,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   }  // query tiles
   fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
@@ -357,7 +383,7 @@ bool attention_tc_supported(const AttnParams& p) {
 
 int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
   if (p.B == 0 || p.T == 0) return 0;
-  const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + 8 * kDP * 128 + 1024 + 64;
+  const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + 8 * kDP * 128 + 1024 + 64 + 2 * 128 * 2 * 4;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

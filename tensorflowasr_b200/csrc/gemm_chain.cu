@@ -58,7 +58,8 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* acc2_empty = acc2_full + 1;
   uint64_t* r_full = acc2_empty + 1;     // residual tile landed in the (recycled) X slabs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 1);
-  float* statbuf = reinterpret_cast<float*>(tmem_slot + 4);   // [128 rows][2 halves][4] LayerNorm partial sums
+  float* statbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [128][2][4] LN partial sums
+  float* pcache = statbuf + 128 * 2 * 4;                      // bias1[N1] | bias2 | ln1_g | ln1_b | ln2_g | ln2_b  (N2 each)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.n_chunks;
@@ -208,6 +209,28 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int cu0 = half ? kSplit : 0, cu1 = half ? kUnits : kSplit;
     uint32_t full_cnt[2] = {0, 0};
     uint32_t tphase = 0;
+    // every per-column parameter is copied to shared memory once, while the first MMAs are in flight: the epilogue
+    // warps would otherwise pay a first-touch L2 round trip per chunk for them
+    const int n1 = nch * CH;
+    const int et = threadIdx.x - 64;                   // 0..255 among the epilogue warps
+    for (int i = et; i < n1; i += 256) pcache[i] = p.bias1[i];
+    for (int i = et; i < N2; i += 256) {
+      pcache[n1 + i] = p.ep.bias[i];
+      pcache[n1 + N2 + i] = p.ep.ln1_g[i];
+      pcache[n1 + 2 * N2 + i] = p.ep.ln1_b[i];
+      pcache[n1 + 3 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_g[i] : 0.f;
+      pcache[n1 + 4 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_b[i] : 0.f;
+    }
+    epi_bar_sync<256>();
+    TcParams ep = p.ep;
+    ep.bias = pcache + n1;
+    ep.ln1_g = pcache + n1 + N2;
+    ep.ln1_b = pcache + n1 + 2 * N2;
+    if (p.ep.ln2_g) {
+      ep.ln2_g = pcache + n1 + 3 * N2;
+      ep.ln2_b = pcache + n1 + 4 * N2;
+    }
+    const float* bias1 = pcache;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
       for (int j = 0; j < nch; ++j) {
         const int a = j & 1;
@@ -229,7 +252,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const int u = cu0 + i;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias1 + j * CH + 16 * u + 4 * q));
+              const float4 b = *reinterpret_cast<const float4*>(bias1 + j * CH + 16 * u + 4 * q);
               raw[i][4 * q + 0] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 0]) + b.x));
               raw[i][4 * q + 1] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 1]) + b.y));
               raw[i][4 * q + 2] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 2]) + b.z));
@@ -254,7 +277,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       // the weight ring is idle from here until the next tile's first load (the producer is gated on acc2_empty): use it as
       // the second staging tile so the C store is not waited for before C2 is produced
       constexpr bool kRingFits = (size_t)STAGES * kRing >= (size_t)BM * ((N2 + 31) / 32) * 128;
-      epilogue_ln_tma<EPI, N2, BM, 2>(p.ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM, quad * 32 + lane,
+      epilogue_ln_tma<EPI, N2, BM, 2>(ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM, quad * 32 + lane,
                                       warp == 2 && lane == 0, half, statbuf, kRingFits ? ring : nullptr);
       tcgen05_fence_before();
       __syncwarp();
@@ -273,7 +296,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
 template <int CH, int N2, int STAGES>
 size_t chain_smem(int kb1) {
-  return (size_t)kb1 * 128 * 128 + (size_t)STAGES * (CH > N2 ? CH : N2) * 128 + 1024 + 256 + 128 * 2 * 4 * 4 /*LayerNorm partial sums*/;
+  return (size_t)kb1 * 128 * 128 + (size_t)STAGES * (CH > N2 ? CH : N2) * 128 + 1024 + 256 + 128 * 2 * 4 * 4 /*LayerNorm partial sums*/ + (1024 + 5 * 256) * 4 /*parameter cache*/ + 16;
 }
 
 template <int EPI, int CH, int N2, int STAGES>

@@ -431,7 +431,7 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
     tmem_ld_wait();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + 16 * u + 4 * q));
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + 16 * u + 4 * q);   // (may point to shared memory)
       float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
       float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
       if (has_resid) {
@@ -457,8 +457,8 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
   auto affine = [&](float* v, float mean, float rstd, const float* g, const float* be, int u) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + 16 * u + 4 * q));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + 16 * u + 4 * q));
+      const float4 gg = *reinterpret_cast<const float4*>(g + 16 * u + 4 * q);
+      const float4 bb = *reinterpret_cast<const float4*>(be + 16 * u + 4 * q);
       v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
       v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
     }
