@@ -135,6 +135,13 @@ B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const floa
                                     float alpha, int epilogue, const float* ln1_g, const float* ln1_b, const float* ln2_g,
                                     const float* ln2_b, float eps, void* stream);
 
+/* Same contract as b200asr_debug_chain through the cluster-pair variant (hidden dimension split across two CTAs, partial
+ * accumulators exchanged through distributed shared memory); N2 = 144, N1 = 288 or 576 only. */
+B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const float* W1, const float* b1, const float* W2,
+                                         const float* b2, const float* resid, float* C, float* C2, int M, int K1, int N1, int N2,
+                                         float alpha, int epilogue, const float* ln1_g, const float* ln1_b, const float* ln2_g,
+                                         const float* ln2_b, float eps, void* stream);
+
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);
 

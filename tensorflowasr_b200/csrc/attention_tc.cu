@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   fence_before();
   __syncthreads();
   fence_after();
+  pdl_trigger();   // TMEM is allocated: the next kernel's CTAs may start their prologue
+  pdl_wait();      // QKV (written by the previous kernel) is complete and visible
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;            // columns [0, 256)
   const uint32_t tmem_O = tmem_base + kKT;      // columns [256, 320)
@@ -404,7 +406,7 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
     pp.dbg = dbg;
     cudaMemset(dbg, 0, sizeof(long long) * 64);
   }
-  attention_tc_kernel<<<grid, kThreadsA, smem, stream>>>(pp);
+  B200_CUDA_OK(launch_k(attention_tc_kernel, grid, dim3(kThreadsA), smem, stream, pp));
   B200_CUDA_OK(cudaGetLastError());
   if (dbg_on) {
     long long hb[64];

@@ -11,6 +11,8 @@ namespace {
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, int M, int D,
                                                         float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -50,6 +52,8 @@ constexpr int kAttQ = 64, kAttK = 64;
 template <int CPT>
 __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p, int dhs) {
   extern __shared__ __align__(16) float sm[];
+  pdl_trigger();
+  pdl_wait();
   const int dh = p.dh;
   float* Qs = sm;                      // [64][dhs]
   float* Ks = Qs + kAttQ * dhs;        // [64][dhs]
@@ -188,6 +192,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p, int 
 
 // generic fallback (any kernel size)
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwConvParams p) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = (size_t)p.B * p.T * p.D;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % p.D);
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwConvParams p) {
 // global access is a coalesced row of D floats.  grid (ceil(T/TT), B), block = D rounded up to a warp multiple.
 template <int K, int TT>
 __global__ void __launch_bounds__(512) dwconv_reg_kernel(const DwConvParams p) {
+  pdl_trigger();
   const int c = threadIdx.x;
   if (c >= p.D) return;
   const int b = blockIdx.y;
@@ -215,7 +222,8 @@ __global__ void __launch_bounds__(512) dwconv_reg_kernel(const DwConvParams p) {
   const float* xb = p.x + (size_t)b * p.T * p.D + c;
   float w[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) w[j] = p.w[j * p.D + c];
+  for (int j = 0; j < K; ++j) w[j] = p.w[j * p.D + c];   // taps are weights: fetched while the producer of x is still running
+  pdl_wait();
   float in[TT + K - 1];
 #pragma unroll
   for (int i = 0; i < TT + K - 1; ++i) {
@@ -241,7 +249,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
     return 1;
   }
   if (M == 0) return 0;
-  layernorm_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(x, gamma, beta, y, M, D, eps);
+  B200_CUDA_OK(launch_k(layernorm_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, x, gamma, beta, y, M, D, eps));
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -267,10 +275,10 @@ int launch_attention(const AttnParams& p, cudaStream_t stream) {
     configured = true;
   }
   switch (cpt) {
-    case 1: attention_kernel<1><<<grid, 256, smem, stream>>>(p, dhs); break;
-    case 2: attention_kernel<2><<<grid, 256, smem, stream>>>(p, dhs); break;
-    case 3: attention_kernel<3><<<grid, 256, smem, stream>>>(p, dhs); break;
-    default: attention_kernel<4><<<grid, 256, smem, stream>>>(p, dhs); break;
+    case 1: B200_CUDA_OK(launch_k(attention_kernel<1>, grid, dim3(256), smem, stream, p, dhs)); break;
+    case 2: B200_CUDA_OK(launch_k(attention_kernel<2>, grid, dim3(256), smem, stream, p, dhs)); break;
+    case 3: B200_CUDA_OK(launch_k(attention_kernel<3>, grid, dim3(256), smem, stream, p, dhs)); break;
+    default: B200_CUDA_OK(launch_k(attention_kernel<4>, grid, dim3(256), smem, stream, p, dhs)); break;
   }
   B200_CUDA_OK(cudaGetLastError());
   return 0;
@@ -282,14 +290,14 @@ int launch_dwconv(const DwConvParams& p, cudaStream_t stream) {
   const int threads = ceil_div(p.D, 32) * 32;
   if (p.K == 32 && threads <= 512) {
     constexpr int TT = 8;
-    dwconv_reg_kernel<32, TT><<<dim3(ceil_div(p.T, TT), p.B), threads, 0, stream>>>(p);
+    B200_CUDA_OK(launch_k(dwconv_reg_kernel<32, TT>, dim3(ceil_div(p.T, TT), p.B), dim3(threads), 0, stream, p));
   } else if (p.K == 5 && threads <= 512) {
     constexpr int TT = 16;
-    dwconv_reg_kernel<5, TT><<<dim3(ceil_div(p.T, TT), p.B), threads, 0, stream>>>(p);
+    B200_CUDA_OK(launch_k(dwconv_reg_kernel<5, TT>, dim3(ceil_div(p.T, TT), p.B), dim3(threads), 0, stream, p));
   } else {
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    dwconv_kernel<<<blocks, 256, 0, stream>>>(p);
+    B200_CUDA_OK(launch_k(dwconv_kernel, dim3(blocks), dim3(256), 0, stream, p));
   }
   B200_CUDA_OK(cudaGetLastError());
   return 0;

@@ -23,6 +23,50 @@ extern thread_local char g_errbuf[512];
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ------------------------------------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the schedule is launched with cudaLaunchAttributeProgrammaticStreamSerialization (also inside the captured
+// CUDA graph): a kernel calls pdl_trigger() once its prologue resources are taken (TMEM allocated), which lets the NEXT
+// kernel's CTAs start and run THEIR prologue (barrier init, TMEM alloc, tensor-map prefetch, parameter caches) under this
+// kernel's main body; pdl_wait() then blocks until the previous grid has completed and its writes are visible.  Rule: no
+// global-memory access that depends on (or could disturb) an earlier kernel before pdl_wait(); trigger only AFTER tcgen05.alloc
+// (a dependent CTA must never hold TMEM that a not-yet-allocated CTA of the primary still needs).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern bool g_pdl_enabled;   // engine.cu; B200ASR_NO_PDL=1 in the environment turns the launch attribute off
+
+// cluster_x > 1: thread-block cluster of that many CTAs along x (grid.x must be a multiple of it)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_pdl_enabled) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return launch_k_cluster(kern, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
+}
+
 // TensorFlow "SAME" padding (== ONNX SAME_UPPER): out = ceil(in/stride), pad_before = total/2.
 struct SamePad {
   int out, before, after;

@@ -11,6 +11,8 @@ namespace {
 // warp per frame
 __global__ void __launch_bounds__(256) frame_argmax_kernel(const float* __restrict__ logits, int rows, int V,
                                                            int* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) frame_argmax_kernel(const float* __restri
 __global__ void __launch_bounds__(32) ctc_collapse_kernel(const int* __restrict__ am, const int* __restrict__ lengths,
                                                           int T, int blank, int* __restrict__ ids,
                                                           int* __restrict__ out_len) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, lane = threadIdx.x;
   const int len = lengths ? min(lengths[b], T) : T;
   const int* a = am + (size_t)b * T;
@@ -68,9 +72,9 @@ int launch_ctc_greedy(const float* logits, const int* lengths, int B, int T, int
                       int* out_len, cudaStream_t stream) {
   if (B == 0) return 0;
   if (T > 0) {
-    frame_argmax_kernel<<<ceil_div(B * T, 8), 256, 0, stream>>>(logits, B * T, V, frame_argmax);
+    B200_CUDA_OK(launch_k(frame_argmax_kernel, dim3(ceil_div(B * T, 8)), dim3(256), 0, stream, logits, B * T, V, frame_argmax));
   }
-  ctc_collapse_kernel<<<B, 32, 0, stream>>>(frame_argmax, lengths, T, blank, ids, out_len);
+  B200_CUDA_OK(launch_k(ctc_collapse_kernel, dim3(B), dim3(32), 0, stream, (const int*)frame_argmax, lengths, T, blank, ids, out_len));
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

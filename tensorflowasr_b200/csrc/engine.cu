@@ -12,6 +12,7 @@
 
 namespace b200asr {
 thread_local char g_errbuf[512] = {0};
+bool g_pdl_enabled = true;
 }
 
 using namespace b200asr;
@@ -51,7 +52,9 @@ struct b200asr_engine {
   // frontend
   const float *window = nullptr, *melw = nullptr;
   float2* twiddle = nullptr;
-  int *mel_lo = nullptr, *mel_hi = nullptr;
+  int *mel_lo = nullptr, *mel_hi = nullptr, *mel_off = nullptr;
+  float* mel_wc = nullptr;
+  int mel_nnz = 0;
   // subsampling
   const float *c1w, *c1b, *c2w, *c2b, *linw, *linb;
   std::vector<BlockW> enc_blocks, ctc_blocks;
@@ -63,6 +66,7 @@ struct b200asr_engine {
   int64_t launches = 0;
   std::string err;
   bool use_chain = true;   // chained FFN / conv-tail kernel (B200ASR_NO_CHAIN=1 in the environment turns it off)
+  bool use_pair = true;    // ... with the hidden dimension split across a 2-CTA cluster (B200ASR_NO_PAIR=1 turns it off)
   void* beam_ws = nullptr;
   size_t beam_ws_bytes = 0;
   cudaStream_t own_stream = nullptr;
@@ -280,6 +284,10 @@ int chain_resid_ln(Ctx& c, const float* X, int K1, const float* W1, const float*
   cp.N1 = N1; cp.N2 = D; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1.g; cp.ln1_b = ln1.b; cp.ln_eps = eps;
   if (ln2) { cp.ln2_g = ln2->g; cp.ln2_b = ln2->b; }
   const int epi = ln2 ? EPI_RESID_LN2 : EPI_RESID_LN;
+  if (c.h->use_chain && c.h->use_pair && tc_chain_pair_supported(cp, epi)) {
+    c.h->launches++;
+    return launch_gemm_chain_pair(c.h->tc, cp, epi, c.s);
+  }
   if (c.h->use_chain && tc_chain_supported(cp, epi)) {
     c.h->launches++;
     return launch_gemm_chain(c.h->tc, cp, epi, c.s);
@@ -352,7 +360,7 @@ int run_frontend(Ctx& c, const float* wav, const Shapes& s, const Buffers& b, fl
   b200asr_handle h = c.h;
   FrontendParams fp{};
   fp.wav = wav; fp.window = h->window; fp.twiddle = h->twiddle; fp.melw = h->melw; fp.mel_lo = h->mel_lo;
-  fp.mel_hi = h->mel_hi; fp.power = b.power; fp.pmax = b.pmax; fp.mel = mel_out; fp.B = s.B; fp.L = s.L; fp.T = s.T;
+  fp.mel_hi = h->mel_hi; fp.mel_off = h->mel_off; fp.mel_wc = h->mel_wc; fp.mel_nnz = h->mel_nnz; fp.power = b.power; fp.pmax = b.pmax; fp.mel = mel_out; fp.B = s.B; fp.L = s.L; fp.T = s.T;
   fp.pad_left = s.pad_left; fp.hop = h->cfg.hop; fp.power_stride = kPowerStride; fp.n_mels = h->cfg.n_mels; fp.mode = 0;
   h->launches += 3;
   return launch_frontend(fp, c.s);
@@ -471,6 +479,17 @@ int with_graph(b200asr_handle h, cudaStream_t s, const GraphKey& key, Body body)
     if (e != cudaSuccess) {
       snprintf(g_errbuf, sizeof(g_errbuf), "cudaStreamEndCapture: %s", cudaGetErrorString(e));
       return fail_cuda(h);
+    }
+    if (getenv("B200ASR_GRAPH_DBG")) {   // how many kernel->kernel edges were captured as programmatic (PDL) dependencies?
+      size_t ne = 0;
+      if (cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne > 0) {
+        std::vector<cudaGraphNode_t> from(ne), to(ne);
+        std::vector<cudaGraphEdgeData> ed(ne);
+        size_t nprog = 0;
+        if (cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
+          for (size_t i = 0; i < ne; ++i) nprog += (ed[i].type == cudaGraphDependencyTypeProgrammatic);
+        fprintf(stderr, "b200asr graph: %zu edges, %zu programmatic\n", ne, nprog);
+      }
     }
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
@@ -604,6 +623,20 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
     lo[m] = l;
     hi[m] = r;
   }
+  // compact band weights of the (sparse, triangular) mel filters, staged in shared memory by db_mel_kernel
+  std::vector<int> off(c.n_mels + 1, 0);
+  for (int m = 0; m < c.n_mels; ++m) off[m + 1] = off[m] + (hi[m] - lo[m]);
+  std::vector<float> wc(std::max(off[c.n_mels], 1), 0.f);
+  for (int m = 0; m < c.n_mels; ++m)
+    for (int k = lo[m]; k < hi[m]; ++k) wc[off[m] + k - lo[m]] = melw_host[(size_t)k * c.n_mels + m];
+  h->mel_nnz = off[c.n_mels];
+  if (cudaMalloc(&h->mel_off, sizeof(int) * (c.n_mels + 1)) != cudaSuccess ||
+      cudaMalloc(&h->mel_wc, sizeof(float) * wc.size()) != cudaSuccess ||
+      cudaMemcpy(h->mel_off, off.data(), sizeof(int) * (c.n_mels + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->mel_wc, wc.data(), sizeof(float) * wc.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: device allocation of the mel tables failed");
+    return bail(1);
+  }
   if (cudaMalloc(&h->twiddle, sizeof(float2) * c.n_dft) != cudaSuccess ||
       cudaMalloc(&h->mel_lo, sizeof(int) * c.n_mels) != cudaSuccess ||
       cudaMalloc(&h->mel_hi, sizeof(int) * c.n_mels) != cudaSuccess ||
@@ -615,6 +648,8 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
   }
   if (tc_init(&h->tc) != 0) return bail(1);
   if (const char* e = getenv("B200ASR_NO_CHAIN")) h->use_chain = !(e[0] == '1');
+  if (const char* e = getenv("B200ASR_NO_PDL")) g_pdl_enabled = !(e[0] == '1');
+  if (const char* e = getenv("B200ASR_NO_PAIR")) h->use_pair = !(e[0] == '1');
   *out = h;
   return 0;
 }
@@ -628,6 +663,8 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   if (h->twiddle) cudaFree(h->twiddle);
   if (h->mel_lo) cudaFree(h->mel_lo);
   if (h->mel_hi) cudaFree(h->mel_hi);
+  if (h->mel_off) cudaFree(h->mel_off);
+  if (h->mel_wc) cudaFree(h->mel_wc);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->beam_ws) cudaFree(h->beam_ws);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -952,6 +989,20 @@ B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const floa
   if (!tc_chain_supported(cp, epilogue)) return fail(h, "b200asr_debug_chain: shape not supported by the chained kernel");
   h->launches++;
   ENG_TRY(h, launch_gemm_chain(h->tc, cp, epilogue, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Test hook: the cluster-pair variant of the chained kernel (same arguments).
+B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const float* W1, const float* b1, const float* W2, const float* b2,
+                             const float* resid, float* C, float* C2, int M, int K1, int N1, int N2, float alpha, int epilogue,
+                             const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream) {
+  if (!h) return 1;
+  ChainGemmParams cp{};
+  cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;
+  cp.N2 = N2; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1_g; cp.ln1_b = ln1_b; cp.ln2_g = ln2_g; cp.ln2_b = ln2_b; cp.ln_eps = eps;
+  if (!tc_chain_pair_supported(cp, epilogue)) return fail(h, "b200asr_debug_chain_pair: shape not supported by the cluster-pair kernel");
+  h->launches++;
+  ENG_TRY(h, launch_gemm_chain_pair(h->tc, cp, epilogue, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -7,6 +7,9 @@
 // utterance.  HBM-bound by design: reads the waveform once (frames overlap in L1/L2), writes the power
 // spectrogram once; the dB + mel kernel re-reads it once after the per-utterance max is known.
 #include "kernels.cuh"
+#include "stft_warp.cuh"
+
+#include <cstdlib>
 
 namespace b200asr {
 
@@ -27,6 +30,8 @@ __global__ void __launch_bounds__(256) stft_power_kernel(const float* __restrict
   __shared__ float2 tw[kNfft];
   __shared__ float red[8];
 
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 2;
@@ -106,6 +111,58 @@ __global__ void __launch_bounds__(256) stft_power_kernel(const float* __restrict
   }
 }
 
+// Warp-per-FFT variant (stft_warp.cuh): each warp transforms kSwPairs frame pairs with a register-resident 32 x 32 four-step
+// FFT; the only shared-memory traffic is one transposed exchange and the natural-order spectrum, both warp-private and
+// bank-conflict free, and there is no block barrier inside the transform.  grid (ceil(pairs / (kSwWarps*kSwPairs)), B).
+constexpr int kSwWarps = 8, kSwPairs = 2;
+__global__ void __launch_bounds__(kSwWarps * 32) stft_power_warp_kernel(const float* __restrict__ wav, const float* __restrict__ window,
+                                                                        const float2* __restrict__ twiddle, float* __restrict__ power,
+                                                                        unsigned int* __restrict__ pmax, int L, int T, int pad_left, int hop,
+                                                                        int ps) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  float2* tw = reinterpret_cast<float2*>(sw_smem);            // [1024]
+  float* win = reinterpret_cast<float*>(tw + kNfft);          // [1024]
+  __shared__ float red[kSwWarps];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float2* sb = reinterpret_cast<float2*>(win + kNfft) + warp * kSwTile;
+  pdl_trigger();
+  for (int i = tid; i < kNfft; i += kSwWarps * 32) {          // constant tables: staged while the previous kernel may still run
+    tw[i] = twiddle[i];
+    win[i] = window[i];
+  }
+  __syncthreads();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const float* w = wav + (size_t)b * L;
+  float vmax = 0.0f;
+#pragma unroll 1
+  for (int q = 0; q < kSwPairs; ++q) {
+    const int pair = (blockIdx.x * kSwPairs + q) * kSwWarps + warp;   // a CTA's warps take consecutive frame pairs (they share samples in L1)
+    const int t0 = 2 * pair;
+    if (t0 < T) {                                                     // warp-uniform
+      const bool has_second = (t0 + 1) < T;
+      stft_pass_a(lane, w, L, t0 * hop - pad_left, hop, has_second, win, tw, sb);
+      __syncwarp();
+      float2 v[32];
+      stft_pass_b_load(lane, sb, v);
+      __syncwarp();
+      stft_pass_b_store(lane, v, sb);
+      __syncwarp();
+      float* pa = power + ((size_t)b * T + t0) * ps;
+      vmax = fmaxf(vmax, stft_untangle(lane, sb, pa, pa + ps, has_second));
+      __syncwarp();
+    }
+  }
+  vmax = warp_max(vmax);
+  if (lane == 0) red[warp] = vmax;
+  __syncthreads();
+  if (tid < 32) {
+    float m = (tid < kSwWarps) ? red[tid] : 0.0f;
+    m = warp_max(m);
+    if (tid == 0) atomicMax(pmax + b, __float_as_uint(m));    // non-negative floats order like unsigned ints
+  }
+}
+
 // 10*log(max(p,1e-10))/ln(10) exactly as backend_keras.py:15 writes it in fp32.
 __device__ __forceinline__ float to_db(float p) { return 10.0f * logf(fmaxf(p, 1e-10f)) / 2.302585093f; }
 
@@ -117,6 +174,8 @@ __global__ void __launch_bounds__(256) db_mel_kernel(const float* __restrict__ p
                                                      const int* __restrict__ mel_hi, float* __restrict__ mel, int T, int ps,
                                                      int n_mels, int mode) {
   __shared__ float db[FR][kBins + 3];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
   const int tid = threadIdx.x;
@@ -147,15 +206,97 @@ __global__ void __launch_bounds__(256) db_mel_kernel(const float* __restrict__ p
   }
 }
 
+
+// Second-generation dB + mel kernel.  FR frames per CTA; every thread issues all of its power loads before the first use
+// (the first version exposed one DRAM round trip per element), dB through lg2.approx (10 log10 p = 3.0103 log2 p; the
+// approximation error is < 1e-5 dB against the 5e-3 dB test tolerance), and the sparse triangular mel filters are staged in
+// shared memory as compact band weights before griddepcontrol.wait (they are constants).
+constexpr int kMelMaxNnz = 1536, kMelMaxFilters = 128;
+// dB differences are formed in the log2 domain, (log2 p - log2 pmax) * 3.0103: the subtraction of equal values is exactly 0
+// (a product-then-subtract form lets the compiler contract one side into an FMA and breaks "the loudest bin is 0 dB").
+__device__ __forceinline__ float log2_floor(float p) { return __log2f(fmaxf(p, 1e-10f)); }
+
+template <int FR>
+__global__ void __launch_bounds__(256) db_mel_fast_kernel(const float* __restrict__ power, const unsigned int* __restrict__ pmax,
+                                                          const int* __restrict__ mel_lo, const int* __restrict__ mel_off,
+                                                          const float* __restrict__ mel_wc, int nnz, float* __restrict__ mel, int T, int ps,
+                                                          int n_mels, int mode) {
+  __shared__ float db[FR][kBins + 3];
+  __shared__ float wc_s[kMelMaxNnz];
+  __shared__ int lo_s[kMelMaxFilters], off_s[kMelMaxFilters + 1];
+  const int tid = threadIdx.x;
+  pdl_trigger();
+  for (int i = tid; i < nnz; i += 256) wc_s[i] = mel_wc[i];
+  for (int i = tid; i < n_mels; i += 256) lo_s[i] = mel_lo[i];
+  for (int i = tid; i <= n_mels; i += 256) off_s[i] = mel_off[i];
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FR;
+  const float maxlg = (mode == 0) ? log2_floor(__uint_as_float(pmax[b])) : 0.0f;
+  constexpr int NIT = (FR * kBins + 255) / 256;
+  float pv[NIT];
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int i = tid + 256 * j;
+    const int f = i / kBins, k = i - f * kBins;
+    pv[j] = (i < FR * kBins && t0 + f < T) ? __ldg(power + ((size_t)b * T + t0 + f) * ps + k) : 1.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int i = tid + 256 * j;
+    const int f = i / kBins, k = i - f * kBins;
+    if (i < FR * kBins) {
+      float vdb;
+      if (mode == 0) vdb = fmaxf(3.0102999566398120f * (log2_floor(pv[j]) - maxlg), -80.0f);
+      else vdb = 0.30102999566398120f * log2_floor(pv[j]);
+      db[f][k] = vdb;
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < FR * n_mels; o += 256) {
+    const int f = o / n_mels, m = o - f * n_mels;
+    const int t = t0 + f;
+    if (t >= T) continue;
+    const int lo = lo_s[m], w0 = off_s[m], n = off_s[m + 1] - w0;
+    float acc = 0.0f;
+    for (int k = 0; k < n; ++k) acc = fmaf(db[f][lo + k], wc_s[w0 + k], acc);
+    mel[((size_t)b * T + t) * n_mels + m] = acc;
+  }
+}
+
 int launch_frontend(const FrontendParams& p, cudaStream_t stream) {
   B200_CUDA_OK(cudaMemsetAsync(p.pmax, 0, sizeof(unsigned int) * p.B, stream));
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("B200ASR_STFT_LEGACY");
+    legacy = (e && e[0] == '1') ? 1 : 0;
+  }
   dim3 g1(ceil_div(p.T, 2), p.B);
-  stft_power_kernel<<<g1, 256, 0, stream>>>(p.wav, p.window, p.twiddle, p.power, p.pmax, p.L, p.T, p.pad_left, p.hop,
-                                             p.power_stride);
-  constexpr int FR = 4;
-  dim3 g2(ceil_div(p.T, FR), p.B);
-  db_mel_kernel<FR><<<g2, 256, 0, stream>>>(p.power, p.pmax, p.melw, p.mel_lo, p.mel_hi, p.mel, p.T, p.power_stride,
-                                            p.n_mels, p.mode);
+  if (!legacy) {
+    const size_t smem = sizeof(float2) * kNfft + sizeof(float) * kNfft + sizeof(float2) * kSwTile * kSwWarps;
+    static bool configured = false;
+    if (!configured) {
+      B200_CUDA_OK(cudaFuncSetAttribute(stft_power_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    dim3 gw(ceil_div(ceil_div(p.T, 2), kSwWarps * kSwPairs), p.B);
+    B200_CUDA_OK(launch_k(stft_power_warp_kernel, gw, dim3(kSwWarps * 32), smem, stream, p.wav, p.window, p.twiddle, p.power, p.pmax, p.L, p.T,
+                          p.pad_left, p.hop, p.power_stride));
+  } else {
+    B200_CUDA_OK(launch_k(stft_power_kernel, g1, dim3(256), 0, stream, p.wav, p.window, p.twiddle, p.power, p.pmax, p.L, p.T, p.pad_left,
+                          p.hop, p.power_stride));
+  }
+  if (!legacy && p.mel_wc != nullptr && p.mel_nnz <= kMelMaxNnz && p.n_mels <= kMelMaxFilters) {
+    constexpr int FR = 8;
+    dim3 g2(ceil_div(p.T, FR), p.B);
+    B200_CUDA_OK(launch_k(db_mel_fast_kernel<FR>, g2, dim3(256), 0, stream, (const float*)p.power, (const unsigned int*)p.pmax, p.mel_lo,
+                          p.mel_off, p.mel_wc, p.mel_nnz, p.mel, p.T, p.power_stride, p.n_mels, p.mode));
+  } else {
+    constexpr int FR = 4;
+    dim3 g2(ceil_div(p.T, FR), p.B);
+    B200_CUDA_OK(launch_k(db_mel_kernel<FR>, g2, dim3(256), 0, stream, (const float*)p.power, (const unsigned int*)p.pmax, p.melw, p.mel_lo,
+                          p.mel_hi, p.mel, p.T, p.power_stride, p.n_mels, p.mode));
+  }
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

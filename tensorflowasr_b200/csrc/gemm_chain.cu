@@ -99,6 +99,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc2 = tmem_base + 2 * CH;
+  pdl_trigger();   // TMEM is allocated: the next kernel's CTAs may start their prologue under this kernel's main body
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -111,15 +112,24 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tma_load_2d(map, &full_bar[stage], ring + (size_t)stage * kRing, c0, c1);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
-      auto g1 = [&](int j) { for (int kb = 0; kb < p.kb1; ++kb) ring_load(&map_w1, kb * 32, j * CH, CH * 128); };
+      auto g1 = [&](int j, int kb0 = 0) { for (int kb = kb0; kb < p.kb1; ++kb) ring_load(&map_w1, kb * 32, j * CH, CH * 128); };
       auto g2 = [&](int j) { for (int kb = 0; kb < KB2; ++kb) ring_load(&map_w2, j * CH + kb * 32, 0, N2 * 128); };
+      // the first weight slabs are constants: they are requested BEFORE griddepcontrol.wait, i.e. while the previous kernel
+      // of the schedule is still draining; X and the residual stream (its outputs) only after the wait
+      // (no more than the ring holds: the MMA warp cannot free a stage before X has arrived)
+      bool first = true;
+      const int npre = p.kb1 < STAGES ? p.kb1 : STAGES;
+      if (blockIdx.x < p.num_m_tiles)
+        for (int kb = 0; kb < npre; ++kb) ring_load(&map_w1, kb * 32, 0, CH * 128);
+      pdl_wait();
       for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
         stamp(0);
         mbar_wait(acc2_empty, xphase ^ 1);                    // previous tile's epilogue has left the slabs (they stage its output)
         mbar_expect_tx(x_full, (uint32_t)p.kb1 * kXSlab);
         for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d(&map_x, x_full, xs + (size_t)kb * kXSlab, kb * 32, tile * BM);
         stamp(0);
-        g1(0);
+        g1(0, first ? npre : 0);
+        first = false;
         stamp(0);
         for (int j = 1; j < nch; ++j) { g1(j); stamp(0); g2(j - 1); stamp(0); }
         g2(nch - 1);
@@ -221,6 +231,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       pcache[n1 + 3 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_g[i] : 0.f;
       pcache[n1 + 4 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_b[i] : 0.f;
     }
+    pdl_wait();   // (the parameter cache above only reads weights: it fills while the previous kernel is still running)
     epi_bar_sync<256>();
     TcParams ep = p.ep;
     ep.bias = pcache + n1;
@@ -320,7 +331,7 @@ int launch_chain_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1,
   ChainParams cp2 = cp;
   cp2.dbg = dbg_on ? dbg : nullptr;
   if (dbg_on) cudaMemset(dbg, 0, sizeof(long long) * 192);
-  kern<<<grid, kChainThreads, smem, stream>>>(mx, m1, m2, mr, mc, mc2, cp2);
+  B200_CUDA_OK(launch_k(kern, dim3(grid), dim3(kChainThreads), smem, stream, mx, m1, m2, mr, mc, mc2, cp2));
   B200_CUDA_OK(cudaGetLastError());
   if (dbg_on) {
     long long hbuf[192];

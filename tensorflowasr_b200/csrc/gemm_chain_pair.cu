@@ -1,0 +1,371 @@
+// Chained FFN / conv-tail GEMMs (see gemm_chain.cu) with the HIDDEN dimension split across a cluster of two CTAs.
+//
+// Why: a tcgen05.mma kind::tf32 instruction (M=128, K=8) costs ~132 cycles whatever N <= 144 is (measured, scripts/ubench_mma.cu;
+// the A operand alone is 128 rows x 32 B), so one 128-row tile of the FFN (72 + 72 instructions) holds an SM for ~19 k cycles while
+// the 8000-row activations of the benchmark batch only make 63 tiles for 148 SMs.  Here both CTAs of a cluster work on the SAME 128
+// rows: CTA r streams the W1 rows / W2 columns of hidden chunks [r*n/2, (r+1)*n/2) only, i.e. half of the MMA instructions, half
+// of the weight bytes through its L2 port and half of the activation work.  The two partial [128 x N2] accumulators are
+// combined through distributed shared memory: each CTA ships the 64 rows it does not own to its peer (st.shared::cluster into
+// the dead X slabs, swizzled like the staging tiles so both sides are bank-conflict free), and finishes residual + LayerNorm(s)
+// + TMA stores for its own 64 rows.
+//
+//   warp 0      TMA producer (first weight slabs before griddepcontrol.wait; X; weight ring; the 64-row residual tile)
+//   warp 1      MMA issuer + TMEM owner (acc1 double buffer [0,2CH), partial acc2 [2CH, 2CH+N2))
+//   warps 2-9   activation of every local chunk; then quadrants of the peer's rows ship, quadrants of the own rows finish
+// Cross-CTA protocol (mbarriers, one tile per CTA, so every parity is 0):
+//   xchg_ready  (in the WRITER's smem, arrived remotely by the destination): "my X slabs are dead, you may write into them"
+//   xchg_full   (in the DESTINATION's smem, 4 remote arrivals = the writer's shipping warps): "your peer's partial has landed"
+#include "tc_common.cuh"
+
+namespace b200asr {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kPairThreads = 320;
+constexpr int CH = 144, N2 = 144, STAGES = 6, BM = 128, HR = 64;   // HR: rows finished per CTA
+constexpr uint32_t kXSlab = BM * 128;                              // 16 KB per 32-column slab of X
+constexpr uint32_t kHSlab = HR * 128;                              // 8 KB per slab of a 64-row tile
+constexpr uint32_t kRing = CH * 128;                               // one weight slab
+constexpr int KB2 = (CH + 31) / 32;
+constexpr int KSTEPS2 = CH / 8;
+constexpr int kSlabs = (N2 + 31) / 32;                             // 5
+
+struct PairParams {
+  TcParams ep;
+  const float* bias1;
+  int nl;            // hidden chunks per CTA
+  int kb1;           // ceil(K1 / 32) slabs of X (== kSlabs)
+  int num_m_tiles;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kPairThreads, 1)
+gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                       const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_r,
+                       const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* xs = smem;                                    // X: kSlabs x 16 KB; later [0,40K) residual/output tile, [40K,80K) peer partial
+  uint8_t* xchg = xs + kSlabs * kHSlab;                  // 64-row tile written by the peer CTA
+  uint8_t* ring = xs + (size_t)kSlabs * kXSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * kRing);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* x_full = empty_bar + STAGES;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* acc1_full = x_empty + 1;     // [2]
+  uint64_t* act_done = acc1_full + 2;    // [2]
+  uint64_t* acc2_full = act_done + 2;
+  uint64_t* r_full = acc2_full + 1;
+  uint64_t* xchg_ready = r_full + 1;
+  uint64_t* xchg_full = xchg_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xchg_full + 1);
+  float* statbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [64][2][4]
+  float* pcache = statbuf + HR * 2 * 4;                  // bias1 (local chunks) | bias2 | ln1_g | ln1_b | ln2_g | ln2_b
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t peer = rank ^ 1u;
+  const int tile = blockIdx.x >> 1;
+  const int nl = p.nl;
+  const int j0 = (int)rank * nl;                          // first hidden chunk of this CTA
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c2) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc1_full[a], 1);
+      mbar_init(&act_done[a], 8);
+    }
+    mbar_init(acc2_full, 1);
+    mbar_init(r_full, 1);
+    mbar_init(xchg_ready, 1);
+    mbar_init(xchg_full, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers exist before anything is signalled across the pair
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc2 = tmem_base + 2 * CH;
+  pdl_trigger();               // TMEM is allocated: the next kernel's CTAs may start their prologue
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto ring_load = [&](const CUtensorMap* map, int c0, int c1, uint32_t bytes) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_load_2d(map, &full_bar[stage], ring + (size_t)stage * kRing, c0, c1);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      auto g1 = [&](int j, int kb0) { for (int kb = kb0; kb < p.kb1; ++kb) ring_load(&map_w1, kb * 32, j * CH, CH * 128); };
+      auto g2 = [&](int j) { for (int kb = 0; kb < KB2; ++kb) ring_load(&map_w2, j * CH + kb * 32, 0, N2 * 128); };
+      // weights are constants: the first slabs are requested before griddepcontrol.wait (under the previous kernel's tail)
+      const int npre = p.kb1 < STAGES ? p.kb1 : STAGES;
+      for (int kb = 0; kb < npre; ++kb) ring_load(&map_w1, kb * 32, j0 * CH, CH * 128);
+      pdl_wait();
+      mbar_expect_tx(x_full, (uint32_t)p.kb1 * kXSlab);
+      for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d(&map_x, x_full, xs + (size_t)kb * kXSlab, kb * 32, tile * BM);
+      g1(j0, npre);
+      for (int jj = 1; jj < nl; ++jj) { g1(j0 + jj, 0); g2(j0 + jj - 1); }
+      g2(j0 + nl - 1);
+      // the X slabs are dead once every first-GEMM MMA has retired: their first half takes this CTA's 64 residual rows
+      mbar_wait(x_empty, 0);
+      mbar_expect_tx(r_full, (uint32_t)kSlabs * kHSlab);
+      for (int kb = 0; kb < kSlabs; ++kb) tma_load_2d(&map_r, r_full, xs + (size_t)kb * kHSlab, kb * 32, tile * BM + (int)rank * HR);
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc1 = make_idesc(BM, CH);
+    constexpr uint32_t idesc2 = make_idesc(BM, N2);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t act_cnt[2] = {0, 0};
+    mbar_wait(x_full, 0);
+    tcgen05_fence_after();
+    auto g1 = [&](int jj) {   // acc1[jj&1] = X . W1_chunk^T
+      const uint32_t d = tmem_base + (uint32_t)((jj & 1) * CH);
+      for (int kb = 0; kb < p.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_smem_desc(smem_u32(xs + (size_t)kb * kXSlab));
+          const uint64_t db = make_smem_desc(smem_u32(ring + (size_t)stage * kRing));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+          tcgen05_commit(&empty_bar[stage]);
+          if (kb == p.kb1 - 1) {
+            tcgen05_commit(&acc1_full[jj & 1]);
+            if (jj == nl - 1) tcgen05_commit(x_empty);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    };
+    auto g2 = [&](int jj) {   // acc2 += act(acc1[jj&1]) . W2_chunk^T   (A operand from TMEM)
+      mbar_wait(&act_done[jj & 1], act_cnt[jj & 1] & 1);
+      act_cnt[jj & 1]++;
+      tcgen05_fence_after();
+      const uint32_t a = tmem_base + (uint32_t)((jj & 1) * CH);
+      for (int kb = 0; kb < KB2; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint64_t db = make_smem_desc(smem_u32(ring + (size_t)stage * kRing));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int step = kb * 4 + k;
+            if (step < KSTEPS2) umma_tf32_ts(tmem_acc2, a + (uint32_t)(8 * step), db + (uint64_t)(2 * k), idesc2, (jj > 0 || step > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);
+          if (jj == nl - 1 && kb == KB2 - 1) tcgen05_commit(acc2_full);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    };
+    g1(0);
+    for (int jj = 1; jj < nl; ++jj) { g1(jj); g2(jj - 1); }
+    g2(nl - 1);
+  } else {
+    // ===================================================================== activation, partial exchange, final epilogue (warps 2..9)
+    const int quad = warp & 3;                       // TMEM lane quadrant (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;                // which half of the columns this warp handles
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    constexpr int kUnits = CH / 16;
+    constexpr int kSplit = (kUnits + 1) / 2;
+    const int cu0 = half ? kSplit : 0, cu1 = half ? kUnits : kSplit;
+    uint32_t full_cnt[2] = {0, 0};
+    const int n1 = nl * CH;
+    const int et = threadIdx.x - 64;                   // 0..255 among these warps
+    for (int i = et; i < n1; i += 256) pcache[i] = p.bias1[j0 * CH + i];
+    for (int i = et; i < N2; i += 256) {
+      pcache[n1 + i] = p.ep.bias[i];
+      pcache[n1 + N2 + i] = p.ep.ln1_g[i];
+      pcache[n1 + 2 * N2 + i] = p.ep.ln1_b[i];
+      pcache[n1 + 3 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_g[i] : 0.f;
+      pcache[n1 + 4 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_b[i] : 0.f;
+    }
+    pdl_wait();   // (the parameter cache above only reads weights)
+    epi_bar_sync<256>();
+    TcParams ep = p.ep;
+    ep.bias = pcache + n1;
+    ep.ln1_g = pcache + n1 + N2;
+    ep.ln1_b = pcache + n1 + 2 * N2;
+    if (p.ep.ln2_g) {
+      ep.ln2_g = pcache + n1 + 3 * N2;
+      ep.ln2_b = pcache + n1 + 4 * N2;
+    }
+    const float* bias1 = pcache;
+    for (int jj = 0; jj < nl; ++jj) {
+      const int a = jj & 1;
+      mbar_wait(&acc1_full[a], full_cnt[a] & 1);
+      full_cnt[a]++;
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(a * CH);
+      uint32_t raw[kSplit][16];
+#pragma unroll
+      for (int i = 0; i < kSplit; ++i)
+        if (cu0 + i < cu1) tmem_ld16_nowait(taddr + (uint32_t)(16 * (cu0 + i)), raw[i]);   // warp-uniform predicate
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < kSplit; ++i) {
+        if (cu0 + i < cu1) {
+          const int u = cu0 + i;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(bias1 + jj * CH + 16 * u + 4 * q);
+            raw[i][4 * q + 0] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 0]) + b.x));
+            raw[i][4 * q + 1] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 1]) + b.y));
+            raw[i][4 * q + 2] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 2]) + b.z));
+            raw[i][4 * q + 3] = tf32_rn_bits(swish_fast(__uint_as_float(raw[i][4 * q + 3]) + b.w));
+          }
+          tmem_st16(taddr + (uint32_t)(16 * u), raw[i]);
+        }
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&act_done[a]);
+    }
+    // ---- this CTA's partial accumulator is complete (so every MMA that read the X slabs has retired)
+    mbar_wait(acc2_full, 0);
+    tcgen05_fence_after();
+    if (warp == 2 && lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(xchg_ready), peer));   // peer may write into my slabs
+    const bool owner = ((uint32_t)(quad >> 1) == rank);     // quadrants 0,1 = rows 0..63 (rank 0), quadrants 2,3 = rows 64..127 (rank 1)
+    const int trow = (quad & 1) * 32 + lane;                // row inside the 64-row half
+    if (!owner) {
+      // ---- ship the peer's 64 rows of my partial accumulator into its exchange tile (same swizzled slab layout as the staging tiles)
+      mbar_wait_cluster(xchg_ready, 0);
+      const uint32_t rbase = map_to_cta(smem_u32(xchg), peer);
+#pragma unroll 1
+      for (int u = cu0; u < cu1; ++u) {
+        uint32_t raw[16];
+        tmem_ld16_nowait(tmem_acc2 + lane_addr + (uint32_t)(16 * u), raw);
+        tmem_ld_wait();
+        const int s = u >> 1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int qq = ((u & 1) << 2) | q;
+          const uint32_t off = (uint32_t)(s * kHSlab + trow * 128 + (((qq ^ (trow & 7)) & 7) << 4));
+          st_cluster_v4(rbase + off, __uint_as_float(raw[4 * q + 0]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                        __uint_as_float(raw[4 * q + 3]));
+        }
+      }
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(xchg_full), peer));
+    } else {
+      // ---- finish my 64 rows: x = resid + alpha * (mine + peer's + bias2), LayerNorm(s), TMA stores
+      mbar_wait(r_full, 0);
+      mbar_wait_cluster(xchg_full, 0);
+      epilogue_ln_tma<EPI, N2, HR, 2, 128>(ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM + (int)rank * HR, trow,
+                                           (quad & 1) == 0 && half == 0 && lane == 0, half, statbuf, ring, xchg);
+    }
+    tcgen05_fence_before();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+size_t pair_smem() {
+  return (size_t)kSlabs * kXSlab + (size_t)STAGES * kRing + 1024 + 256 + HR * 2 * 4 * 4 + (2 * CH + 5 * N2) * 4 + 64;
+}
+
+template <int EPI>
+int launch_pair_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mr,
+                  const CUtensorMap& mc, const CUtensorMap& mc2, const PairParams& pp, cudaStream_t stream) {
+  auto kern = gemm_chain_pair_kernel<EPI>;
+  const size_t smem = pair_smem();
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  (void)ctx;
+  B200_CUDA_OK(launch_k_cluster(kern, dim3(2 * pp.num_m_tiles), dim3(kPairThreads), smem, stream, 2, mx, m1, m2, mr, mc, mc2, pp));
+  return 0;
+}
+
+}  // namespace
+
+bool tc_chain_pair_supported(const ChainGemmParams& p, int epilogue) {
+  if (!tc_chain_supported(p, epilogue)) return false;
+  if (p.N2 != N2 || p.K1 <= 128 || p.K1 > 160) return false;
+  const int nch = p.N1 / CH;
+  return p.N1 % CH == 0 && nch >= 2 && nch % 2 == 0 && nch / 2 <= 2;   // pcache holds at most 2 local chunks of bias1
+}
+
+int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream) {
+  if (!ctx.ready) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "gemm_chain_pair: tensor-map encoder not initialised");
+    return 1;
+  }
+  PairParams pp{};
+  pp.ep.bias = p.bias2; pp.ep.resid = p.resid; pp.ep.C = p.C; pp.ep.C2 = p.C2; pp.ep.M = p.M; pp.ep.N = p.N2; pp.ep.K = p.N1;
+  pp.ep.ldc = p.N2; pp.ep.alpha = p.alpha; pp.ep.ln1_g = p.ln1_g; pp.ep.ln1_b = p.ln1_b; pp.ep.ln2_g = p.ln2_g; pp.ep.ln2_b = p.ln2_b;
+  pp.ep.ln_eps = p.ln_eps;
+  pp.bias1 = p.bias1;
+  pp.nl = p.N1 / CH / 2;
+  pp.kb1 = ceil_div(p.K1, 32);
+  pp.num_m_tiles = ceil_div(p.M, BM);
+  const cuuint32_t ones[2] = {1, 1};
+  CUtensorMap mx, m1, m2, mr, mc, mc2;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K1, (cuuint64_t)p.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.ldx * 4};
+    const cuuint32_t box[2] = {32, BM};
+    if (encode_map(ctx, &mx, p.X, 2, dims, strides, box, ones)) return 1;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K1, (cuuint64_t)p.N1};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.K1 * 4};
+    const cuuint32_t box[2] = {32, CH};
+    if (encode_map(ctx, &m1, p.W1, 2, dims, strides, box, ones)) return 1;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.N1, (cuuint64_t)p.N2};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.N1 * 4};
+    const cuuint32_t box[2] = {32, N2};
+    if (encode_map(ctx, &m2, p.W2, 2, dims, strides, box, ones)) return 1;
+  }
+  {
+    // residual in / outputs: [M, N2] in tiles of 64 rows x 32-column slabs (stores clip the M and column tails)
+    const cuuint64_t dims[2] = {(cuuint64_t)p.N2, (cuuint64_t)p.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.N2 * 4};
+    const cuuint32_t box[2] = {32, HR};
+    if (encode_map(ctx, &mr, p.resid, 2, dims, strides, box, ones)) return 1;
+    if (encode_map(ctx, &mc, p.C, 2, dims, strides, box, ones)) return 1;
+    if (encode_map(ctx, &mc2, p.C2, 2, dims, strides, box, ones)) return 1;
+  }
+  if (epilogue == EPI_RESID_LN) return launch_pair_t<EPI_RESID_LN>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
+  return launch_pair_t<EPI_RESID_LN2>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
+}
+
+}  // namespace b200asr

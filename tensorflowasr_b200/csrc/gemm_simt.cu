@@ -42,6 +42,8 @@ template <int AMODE, int EPI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -122,12 +124,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 template <int AMODE>
 int dispatch(const GemmParams& p, int epi, dim3 grid, cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS: gemm_simt_kernel<AMODE, EPI_BIAS><<<grid, 256, 0, s>>>(p); break;
-    case EPI_BIAS_RELU: gemm_simt_kernel<AMODE, EPI_BIAS_RELU><<<grid, 256, 0, s>>>(p); break;
-    case EPI_BIAS_SWISH: gemm_simt_kernel<AMODE, EPI_BIAS_SWISH><<<grid, 256, 0, s>>>(p); break;
-    case EPI_GLU: gemm_simt_kernel<AMODE, EPI_GLU><<<grid, 256, 0, s>>>(p); break;
-    case EPI_RESID: gemm_simt_kernel<AMODE, EPI_RESID><<<grid, 256, 0, s>>>(p); break;
-    case EPI_NONE: gemm_simt_kernel<AMODE, EPI_NONE><<<grid, 256, 0, s>>>(p); break;
+    case EPI_BIAS: B200_CUDA_OK(launch_k(gemm_simt_kernel<AMODE, EPI_BIAS>, grid, dim3(256), 0, s, p)); break;
+    case EPI_BIAS_RELU: B200_CUDA_OK(launch_k(gemm_simt_kernel<AMODE, EPI_BIAS_RELU>, grid, dim3(256), 0, s, p)); break;
+    case EPI_BIAS_SWISH: B200_CUDA_OK(launch_k(gemm_simt_kernel<AMODE, EPI_BIAS_SWISH>, grid, dim3(256), 0, s, p)); break;
+    case EPI_GLU: B200_CUDA_OK(launch_k(gemm_simt_kernel<AMODE, EPI_GLU>, grid, dim3(256), 0, s, p)); break;
+    case EPI_RESID: B200_CUDA_OK(launch_k(gemm_simt_kernel<AMODE, EPI_RESID>, grid, dim3(256), 0, s, p)); break;
+    case EPI_NONE: B200_CUDA_OK(launch_k(gemm_simt_kernel<AMODE, EPI_NONE>, grid, dim3(256), 0, s, p)); break;
     default: snprintf(g_errbuf, sizeof(g_errbuf), "gemm_simt: bad epilogue %d", epi); return 1;
   }
   return 0;
@@ -140,6 +142,8 @@ int dispatch(const GemmParams& p, int epi, dim3 grid, cudaStream_t s) {
 constexpr int kConv1Rows = 4;
 __global__ void __launch_bounds__(256) conv1_kernel(const Conv1Params p, int groups, int flanes) {
   extern __shared__ float mel_s[];  // [2*ROWS+1][F + 2] with one zero column of padding on each side
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int t1_0 = blockIdx.x * kConv1Rows;
   const int FW = p.F + 2;
@@ -207,7 +211,7 @@ int launch_conv1(const Conv1Params& p, cudaStream_t stream) {
   const int threads = groups * flanes;
   const size_t smem = sizeof(float) * (2 * kConv1Rows + 1) * (p.F + 2);
   dim3 grid(ceil_div(p.T1, kConv1Rows), p.B);
-  conv1_kernel<<<grid, threads, smem, stream>>>(p, groups, flanes);
+  B200_CUDA_OK(launch_k(conv1_kernel, grid, dim3(threads), smem, stream, p, groups, flanes));
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

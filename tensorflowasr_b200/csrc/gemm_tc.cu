@@ -92,8 +92,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
+  pdl_trigger();   // prologue resources are taken (TMEM allocated): the next kernel may start its own prologue
   const uint32_t a_rows_bytes = (p.a_mode == 1) ? (uint32_t)(p.bt * p.F2 * BLOCK_K * 4) : kABytes;
+  // B operand = weights (constants): the first pipeline stages' weight slabs are requested BEFORE griddepcontrol.wait, under
+  // the tail of the previous kernel; everything that kernel produced (A operand, residual) is touched only after the wait
+  int b_prefetched = 0;
+  if (warp == 0 && lane == 0 && (int)blockIdx.x < num_tiles) {
+    const int nt0 = (int)blockIdx.x % p.num_n_tiles;
+    b_prefetched = p.num_k_blocks < kStages ? p.num_k_blocks : kStages;
+    for (int kb = 0; kb < b_prefetched; ++kb) {
+      uint8_t* sb = smem + kb * kStageBytes + kABytes;
+      mbar_expect_tx(&full_bar[kb], a_rows_bytes + kBBytes);
+      if (p.a_mode == 0) {
+        tma_load_2d(&map_b, &full_bar[kb], sb, kb * BLOCK_K, nt0 * BLOCK_N);
+      } else {
+        const int tap = kb / p.kc, j = kb - tap * p.kc;
+        tma_load_2d(&map_b, &full_bar[kb], sb, tap * p.D + j * BLOCK_K, nt0 * BLOCK_N);
+      }
+    }
+  }
+  pdl_wait();      // the previous kernel's outputs (A operand, residual) are complete and visible
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -113,16 +131,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], a_rows_bytes + kBBytes);
+          const bool b_done = b_prefetched > 0;               // this stage's weights (and its expect_tx) were issued before the wait
+          if (b_done) --b_prefetched;
+          else mbar_expect_tx(&full_bar[stage], a_rows_bytes + kBBytes);
           if (p.a_mode == 0) {
             tma_load_2d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, mt * BLOCK_M);
-            tma_load_2d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0);
+            if (!b_done) tma_load_2d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0);
           } else {
             const int b = mt / p.tiles_per_b, tb = mt - b * p.tiles_per_b;
             const int tap = kb / p.kc, j = kb - tap * p.kc;
             const int kh = tap / 3, kw = tap - kh * 3;
             tma_load_4d(&map_a, &full_bar[stage], sa, j * BLOCK_K, kw - p.pad_f, 2 * tb * p.bt + kh - p.pad_t, b);
-            tma_load_2d(&map_b, &full_bar[stage], sb, tap * p.D + j * BLOCK_K, n0);
+            if (!b_done) tma_load_2d(&map_b, &full_bar[stage], sb, tap * p.D + j * BLOCK_K, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -232,7 +252,7 @@ int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, con
   }
   const int tiles = tp.num_m_tiles * tp.num_n_tiles;
   const int grid = tiles < ctx.num_sms ? tiles : ctx.num_sms;
-  kern<<<grid, kThreads, smem_bytes<EPI, BLOCK_N, BLOCK_M>(), stream>>>(ma, mb, lnmaps[0], lnmaps[1], lnmaps[2], tp);
+  B200_CUDA_OK(launch_k(kern, dim3(grid), dim3(kThreads), smem_bytes<EPI, BLOCK_N, BLOCK_M>(), stream, ma, mb, lnmaps[0], lnmaps[1], lnmaps[2], tp));
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

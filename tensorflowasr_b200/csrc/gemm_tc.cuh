@@ -26,5 +26,8 @@ struct ChainGemmParams {
 };
 bool tc_chain_supported(const ChainGemmParams& p, int epilogue);
 int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);
+// same result with the hidden dimension split across a cluster of two CTAs (gemm_chain_pair.cu)
+bool tc_chain_pair_supported(const ChainGemmParams& p, int epilogue);
+int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);
 
 }  // namespace b200asr

@@ -12,6 +12,9 @@ struct FrontendParams {
   const float* melw;       // [513, n_mels]
   const int* mel_lo;       // [n_mels] first bin with non-zero weight
   const int* mel_hi;       // [n_mels] one past last
+  const int* mel_off;      // [n_mels + 1] offsets into mel_wc (compact band weights: mel_wc[mel_off[m] + k - mel_lo[m]] = melw[k, m])
+  const float* mel_wc;     // [mel_nnz]
+  int mel_nnz;
   float* power;            // [B, T, power_stride] scratch
   unsigned int* pmax;      // [B] scratch
   float* mel;              // [B, T, n_mels] out

@@ -379,16 +379,60 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(c1)
                : "memory");
 }
+// ---- thread-block-cluster helpers (gemm_chain_pair.cu)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote writers)
+  const uint32_t addr = smem_u32(bar);
+  unsigned spins = 0;
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > kSpinLimit) {
+      printf("b200asr chain_pair: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // HALVES == 2: two warps share each TMEM lane quadrant and split the row's columns (16-column units [u0, u1)); the LayerNorm
 // partial sums are exchanged through `statbuf` ([ROWS][2][2] floats).  With column-split statistics the variance is the
 // plain E[x^2] - mean^2 (no common shift is available); fp32 is ample for |x| <~ 1e3 over <= 256 columns.
-template <int EPI, int BLOCK_N, int ROWS, int HALVES = 1>
+// NT = threads taking part (named barrier 1).  xchg (optional): a second partial accumulator tile, same layout as `stile`,
+// added to the TMEM accumulator before the bias (gemm_chain_pair.cu: the peer CTA's half of the hidden dimension).
+template <int EPI, int BLOCK_N, int ROWS, int HALVES = 1, int NT = 128 * HALVES>
 __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t taddr, uint8_t* stile, const CUtensorMap* map_c,
                                                 const CUtensorMap* map_c2, int row0, int trow, bool issuer, int half = 0,
-                                                float* statbuf = nullptr, uint8_t* stile2 = nullptr) {
+                                                float* statbuf = nullptr, uint8_t* stile2 = nullptr, uint8_t* xchg = nullptr) {
   constexpr bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
   constexpr int NSLAB = (BLOCK_N + 31) / 32;
   constexpr int NUNIT = BLOCK_N / 16;                    // 16-column units
@@ -405,21 +449,21 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
   // TMA-store the staged tile.  wait_read: block until the store has finished READING shared memory (tile reusable).
   auto store_tile = [&](const CUtensorMap* map, uint8_t* base, bool wait_read) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    epi_bar_sync<128 * HALVES>();
+    epi_bar_sync<NT>();
     if (issuer) {
 #pragma unroll
       for (int s = 0; s < NSLAB; ++s) tma_store_2d(map, base + (size_t)s * ROWS * 128, 32 * s, row0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       if (wait_read) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    if (wait_read) epi_bar_sync<128 * HALVES>();   // the tile(s) may be overwritten again
+    if (wait_read) epi_bar_sync<NT>();   // the tile(s) may be overwritten again
   };
   // combine per-half partial sums (sum, sum of squares) of this row
   auto combine = [&](float& a, float& b, int slot) {
     if (HALVES == 1) return;
     float* mine = statbuf + ((size_t)(active ? trow : 0) * 2 + half) * 4 + slot * 2;
     if (active) { mine[0] = a; mine[1] = b; }
-    epi_bar_sync<128 * HALVES>();
+    epi_bar_sync<NT>();
     const float* other = statbuf + ((size_t)(active ? trow : 0) * 2 + (half ^ 1)) * 4 + slot * 2;
     a += other[0];
     b += other[1];
@@ -434,6 +478,10 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
       const float4 b = *reinterpret_cast<const float4*>(p.bias + 16 * u + 4 * q);   // (may point to shared memory)
       float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
       float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
+      if (xchg != nullptr) {
+        const float4 o = *chunk_ptr_in(xchg, u, q);
+        a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
+      }
       if (has_resid) {
         const float4 r = *chunk_ptr(u, q);
         a0 = r.x + p.alpha * a0; a1 = r.y + p.alpha * a1; a2 = r.z + p.alpha * a2; a3 = r.w + p.alpha * a3;

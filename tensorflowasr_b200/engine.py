@@ -67,6 +67,7 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_debug_gemm_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, ci, vp, vp, vp, vp, cf, vp]
     lib.b200asr_debug_attention.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.b200asr_debug_chain.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, ci, vp, vp, vp, vp, cf, vp]
+    lib.b200asr_debug_chain_pair.argtypes = lib.b200asr_debug_chain.argtypes
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib
@@ -273,14 +274,15 @@ class Engine:
                                                      int(win_back), int(bool(tensor_cores)), self._stream()), "b200asr_debug_attention")
         return out
 
-    def debug_chain(self, X, W1, b1, W2, b2, resid, alpha, epilogue, ln1, ln2=None, eps=1e-3, inplace=True):
-        """Test hook: chained FFN-style kernel.  Returns (C, C2)."""
+    def debug_chain(self, X, W1, b1, W2, b2, resid, alpha, epilogue, ln1, ln2=None, eps=1e-3, inplace=True, pair=False):
+        """Test hook: chained FFN-style kernel (pair=True: the 2-CTA-cluster variant).  Returns (C, C2)."""
         torch = _torch()
         M, K1 = X.shape
         N1, N2 = W1.shape[0], W2.shape[0]
         C = resid if inplace else torch.empty((M, N2), device=self._dev(), dtype=torch.float32)
         C2 = torch.zeros((M, N2), device=self._dev(), dtype=torch.float32)
-        self._check(self.lib.b200asr_debug_chain(
+        fn = self.lib.b200asr_debug_chain_pair if pair else self.lib.b200asr_debug_chain
+        self._check(fn(
             self._h, X.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), resid.data_ptr(), C.data_ptr(),
             C2.data_ptr(), M, K1, N1, N2, float(alpha), int(epilogue), ln1[0].data_ptr(), ln1[1].data_ptr(),
             ln2[0].data_ptr() if ln2 else None, ln2[1].data_ptr() if ln2 else None, float(eps), self._stream()), "b200asr_debug_chain")

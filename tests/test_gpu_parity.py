@@ -290,3 +290,41 @@ def test_reference_facing_asr_surface(ref_wav):
     b.compile(ort_ref.model_dir("offline"))
     assert b.stt(wav_path)[0] == phones
     assert a.recognize_batch(np.stack([ref_wav[:30000], ref_wav[:30000]]))[0] == a.recognize_batch(ref_wav[None, :30000])[0]
+
+
+@pytest.mark.parametrize("pair", [False, True], ids=["chain", "chain_pair"])
+@pytest.mark.parametrize("M,N1", [(8000, 576), (8000, 288), (300, 576), (1, 288), (129, 576), (8064, 288)])
+def test_chained_ffn_kernels_vs_fp64(eng32, torch_mod, pair, M, N1):
+    """The chained FFN / conv-tail tcgen05 kernels (hidden activations in TMEM; `pair`: hidden dimension split across a 2-CTA
+    cluster with the partial sums exchanged through distributed shared memory) against torch fp64:
+    C = resid + 0.5 * (swish(X W1^T + b1) W2^T + b2) with one or two fused LayerNorms.  tf32 tolerance 3e-2 on values ~20."""
+    torch = torch_mod
+    torch.manual_seed(M + N1)
+    K1 = N2 = 144
+
+    def ln(x, g, b, eps=1e-3):
+        mu = x.mean(-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(-1, keepdim=True)
+        return (x - mu) / torch.sqrt(var + eps) * g + b
+
+    X = torch.randn(M, K1, device="cuda")
+    W1 = torch.randn(N1, K1, device="cuda") / K1 ** 0.5
+    b1 = torch.randn(N1, device="cuda") * 0.3
+    W2 = torch.randn(N2, N1, device="cuda") / N1 ** 0.5
+    b2 = torch.randn(N2, device="cuda") * 0.3
+    g1, be1, g2, be2 = (torch.randn(N2, device="cuda") for _ in range(4))
+    for epi in (6, 7):
+        resid = torch.randn(M, N2, device="cuda") * 20
+        hid = X.double() @ W1.double().T + b1.double()
+        hid = hid * torch.sigmoid(hid)
+        x = resid.double() + 0.5 * (hid @ W2.double().T + b2.double())
+        if epi == 6:
+            c_ref, c2_ref = x, ln(x, g1.double(), be1.double())
+        else:
+            c_ref = ln(x, g1.double(), be1.double())
+            c2_ref = ln(c_ref, g2.double(), be2.double())
+        C, C2 = eng32.debug_chain(X, W1, b1, W2, b2, resid, 0.5, epi, (g1, be1), (g2, be2) if epi == 7 else None, pair=pair)
+        torch.cuda.synchronize()
+        assert not torch.isnan(C2).any()
+        assert (C.double() - c_ref).abs().max().item() < 3e-2
+        assert (C2.double() - c2_ref).abs().max().item() < 3e-2

@@ -110,3 +110,22 @@ def test_same_padding_arithmetic():
     assert tf_same_pad(67263, 1024, 160) == (421, 480, 481)
     assert tf_same_pad(1000, 3, 2) == (500, 0, 1) and tf_same_pad(421, 3, 2) == (211, 1, 1)
     assert tf_same_pad(250, 32, 1) == (250, 15, 16)
+
+
+def test_warp_fft_phases_on_host(tmp_path):
+    """csrc/stft_warp.cuh (the 32 x 32 four-step FFT of the STFT kernel) compiled for the HOST and run lane by lane against a
+    direct double-precision DFT: tests/host/stft_warp_host.cu exits 0 when both frames' power spectra agree to 2e-5 of the
+    frame maximum (padding on either side and the odd-frame-count case included)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "stft_warp_host")
+    src = os.path.join(ROOT, "tests", "host", "stft_warp_host.cu")
+    r = subprocess.run([nvcc, "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe, src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max_rel_err" in r.stdout
