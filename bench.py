@@ -282,25 +282,39 @@ def main():
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
-        # roofline of the dominant kernel, timed alone with CUDA events on this stream
+        # roofline of the dominant kernel, timed alone with CUDA events on this stream (back-to-back launches through the C ABI)
         roof = None
         if rank == 0:
             eng.recognize(dev[0], ids, lens)
             torch.cuda.synchronize()
-            stage = "conv2"
-            ms_k, flops, bytes_ = eng.time_stage(stage, BATCH, L, iters=20)
             hbm_peak, tf_peak, how = measured_peaks()
+            traffic = {}
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+            if os.path.isfile(tpath):
+                traffic = json.load(open(tpath))
+            prec = "tf32 (half the bf16 tensor rate)" if args.precision == "tf32" else "fp32 on CUDA cores"
+
+            def stage_line(st, iters=20):
+                m, f, b = eng.time_stage(st, BATCH, L, iters=iters)
+                d = {"ms_per_launch": round(m, 5), "tflops": round(f / (m * 1e-3) / 1e12, 2), "frac_tensor_peak": round(f / (m * 1e-3) / 1e12 / tf_peak, 4),
+                     "gbs": round(b / (m * 1e-3) / 1e9, 1), "frac_hbm_peak": round(b / (m * 1e-3) / 1e9 / hbm_peak, 4),
+                     "flops_per_launch": f, "algorithmic_bytes_per_launch": b, "traffic": traffic.get(st)}
+                return m, f, b, d
+
+            # the chained FFModule kernel (both GEMMs + swish + residual + LayerNorm; 42 of the 121 launches, ~35 % of the step)
+            ms_k, flops, bytes_, _ = stage_line("ffn_chain")
             ach = flops / (ms_k * 1e-3) / 1e12
-            peak = tf_peak if args.precision == "tf32" else None
-            roof = {"kernel": "conv_subsampling conv2 (implicit GEMM M=%d N=144 K=1296, fused bias+ReLU)" % (BATCH * Tp * 20),
+            roof = {"kernel": "FFModule as one chained tcgen05 kernel, cluster-pair variant (M=%d, 144 -> 576 -> 144, swish, 0.5-residual, "
+                              "LayerNorm): 42 of the 121 launches of a step" % (BATCH * Tp),
                     "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}); the kernel computes in "
-                                   f"{'tf32 (half the bf16 tensor rate)' if args.precision == 'tf32' else 'fp32 on CUDA cores'}",
-                    "ms_per_launch": ms_k, "flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_, "traffic": None}
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}); the kernel computes in {prec}",
+                    "ms_per_launch": ms_k, "flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_,
+                    "traffic": traffic.get("ffn_chain"),
+                    "note": "M = 8000 rows is 63 row tiles for 148 SMs and a tf32 tcgen05.mma (M=128, K=8) costs ~132 cycles for any N <= 144 "
+                            "(profiles/r01_ubench_mma_tf32_pacing.txt): the kernel is bound by its MMA instruction count, not by bytes"}
             others = {}
-            for st in ("stft", "ffn_w1", "ffn_w2", "attention", "sub_linear", "ctc_fc"):
-                m, f, b = eng.time_stage(st, BATCH, L, iters=20)
-                others[st] = {"ms": round(m, 4), "tflops": round(f / (m * 1e-3) / 1e12, 2), "gbs": round(b / (m * 1e-3) / 1e9, 1)}
+            for st in ("conv2", "stft", "conv1", "qkv", "attention", "dwconv", "sub_linear", "ctc_fc"):
+                others[st] = stage_line(st)[3]
             roof["other_stages"] = others
 
     t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)

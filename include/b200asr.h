@@ -107,7 +107,9 @@ B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, 
 /* Roofline instrumentation (bench.py): time one stage of the schedule alone, `iters` launches bracketed by CUDA events on
  * `stream`; also returns that launch's algorithmic FLOPs and HBM bytes.  Run b200asr_recognize with the same (B, L) first. */
 enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 = 2, B200ASR_STAGE_STFT = 3,
-       B200ASR_STAGE_SUBLIN = 4, B200ASR_STAGE_ATTENTION = 5, B200ASR_STAGE_CTC_FC = 6 };
+       B200ASR_STAGE_SUBLIN = 4, B200ASR_STAGE_ATTENTION = 5, B200ASR_STAGE_CTC_FC = 6,
+       B200ASR_STAGE_FFN_CHAIN = 7 /* whole FFModule as one chained kernel: both GEMMs + swish + residual + LayerNorm */,
+       B200ASR_STAGE_CONV1 = 8, B200ASR_STAGE_DWCONV = 9, B200ASR_STAGE_QKV = 10 };
 B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, int iters, void* stream, float* ms_per_launch,
                                    double* flops, double* bytes);
 

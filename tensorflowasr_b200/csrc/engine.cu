@@ -911,6 +911,39 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
         *bytes = 4.0 * (M * D + D * cfg.vocab + M * cfg.vocab);
         break;
       }
+      case B200ASR_STAGE_FFN_CHAIN: {
+        const BlockW& w = h->enc_blocks[0];
+        rc = chain_resid_ln(c, b.xn, cfg.dmodel, w.ffn1.w1, w.ffn1.b1, cfg.ff_dim, w.ffn1.w2, w.ffn1.b2, 0.5f, b, s.M, cfg.dmodel, w.mhsa.ln,
+                            nullptr, cfg.ln_eps);
+        *flops = 4.0 * M * D * cfg.ff_dim;
+        *bytes = 4.0 * (4.0 * M * D + 2.0 * D * cfg.ff_dim);   // xn + x in, x + xn out, both weight matrices once
+        break;
+      }
+      case B200ASR_STAGE_CONV1: {
+        Conv1Params c1{};
+        c1.mel = b.mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
+        c1.F1 = h->F1; c1.D = cfg.dmodel; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
+        rc = launch_conv1(c1, st);
+        *flops = 2.0 * 9.0 * s.B * s.T1 * h->F1 * D;
+        *bytes = 4.0 * ((double)s.B * s.T * cfg.n_mels + (double)s.B * s.T1 * h->F1 * D);
+        break;
+      }
+      case B200ASR_STAGE_DWCONV: {
+        DwConvParams dp{};
+        dp.x = b.g; dp.w = h->enc_blocks[0].conv.dww; dp.y = b.att; dp.B = s.B; dp.T = s.T2; dp.D = cfg.dmodel; dp.K = cfg.kernel_size;
+        dp.pad_left = same_pad(s.T2, cfg.kernel_size, 1).before;
+        rc = launch_dwconv(dp, st);
+        *flops = 2.0 * M * D * cfg.kernel_size;
+        *bytes = 4.0 * 2.0 * M * D;
+        break;
+      }
+      case B200ASR_STAGE_QKV: {
+        const int HD = cfg.num_heads * cfg.head_size;
+        rc = gemm(c, b.xn, cfg.dmodel, h->enc_blocks[0].mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, s.M, 3 * HD, cfg.dmodel, EPI_NONE);
+        *flops = 2.0 * M * D * 3.0 * HD;
+        *bytes = 4.0 * (M * D + 3.0 * HD * D + M * 3.0 * HD);
+        break;
+      }
       default:
         rc = 1;
         snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_time_stage: unknown stage %d", stage);

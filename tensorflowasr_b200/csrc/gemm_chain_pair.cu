@@ -5,17 +5,22 @@
 // the 8000-row activations of the benchmark batch only make 63 tiles for 148 SMs.  Here both CTAs of a cluster work on the SAME 128
 // rows: CTA r streams the W1 rows / W2 columns of hidden chunks [r*n/2, (r+1)*n/2) only, i.e. half of the MMA instructions, half
 // of the weight bytes through its L2 port and half of the activation work.  The two partial [128 x N2] accumulators are
-// combined through distributed shared memory: each CTA ships the 64 rows it does not own to its peer (st.shared::cluster into
-// the dead X slabs, swizzled like the staging tiles so both sides are bank-conflict free), and finishes residual + LayerNorm(s)
-// + TMA stores for its own 64 rows.
+// combined through distributed shared memory: each CTA stages the 64 rows it does not own in its (idle) weight ring, swizzled like
+// the staging tiles, and one thread sends them with ONE 40 KB cp.async.bulk.shared::cluster into the peer's dead X slabs
+// (per-lane st.shared::cluster of row fragments measured 4.7 k cycles for the same bytes); each CTA then finishes residual +
+// LayerNorm(s) + TMA stores for its own 64 rows.
 //
 //   warp 0      TMA producer (first weight slabs before griddepcontrol.wait; X; weight ring; the 64-row residual tile)
 //   warp 1      MMA issuer + TMEM owner (acc1 double buffer [0,2CH), partial acc2 [2CH, 2CH+N2))
 //   warps 2-9   activation of every local chunk; then quadrants of the peer's rows ship, quadrants of the own rows finish
 // Cross-CTA protocol (mbarriers, one tile per CTA, so every parity is 0):
-//   xchg_ready  (in the WRITER's smem, arrived remotely by the destination): "my X slabs are dead, you may write into them"
-//   xchg_full   (in the DESTINATION's smem, 4 remote arrivals = the writer's shipping warps): "your peer's partial has landed"
+//   xchg_ready  (in the WRITER's smem, arrived remotely by the destination's producer as soon as its first-GEMM MMAs have
+//               retired): "my X slabs are dead, you may write into them"
+//   xchg_full   (in the DESTINATION's smem: expect_tx by the destination, complete_tx by the writer's bulk copy): "your peer's
+//               partial has landed"
 #include "tc_common.cuh"
+
+#include <cstdlib>
 
 namespace b200asr {
 
@@ -38,6 +43,7 @@ struct PairParams {
   int nl;            // hidden chunks per CTA
   int kb1;           // ceil(K1 / 32) slabs of X (== kSlabs)
   int num_m_tiles;
+  long long* dbg;    // optional timeline of cluster 0 / CTA 0 (B200ASR_PAIR_DBG=1): [role][event] clock64 stamps
 };
 
 template <int EPI>
@@ -71,6 +77,11 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   const int tile = blockIdx.x >> 1;
   const int nl = p.nl;
   const int j0 = (int)rank * nl;                          // first hidden chunk of this CTA
+  int ev = 0;
+  auto stamp = [&](int role) {
+    if (p.dbg && blockIdx.x == 0 && lane == 0 && ev < 32) p.dbg[role * 32 + ev++] = clock64();
+  };
+  if (warp == 0) stamp(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -92,7 +103,7 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     mbar_init(acc2_full, 1);
     mbar_init(r_full, 1);
     mbar_init(xchg_ready, 1);
-    mbar_init(xchg_full, 4);
+    mbar_init(xchg_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -123,16 +134,22 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       // weights are constants: the first slabs are requested before griddepcontrol.wait (under the previous kernel's tail)
       const int npre = p.kb1 < STAGES ? p.kb1 : STAGES;
       for (int kb = 0; kb < npre; ++kb) ring_load(&map_w1, kb * 32, j0 * CH, CH * 128);
+      stamp(0);
       pdl_wait();
+      stamp(0);
       mbar_expect_tx(x_full, (uint32_t)p.kb1 * kXSlab);
       for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d(&map_x, x_full, xs + (size_t)kb * kXSlab, kb * 32, tile * BM);
       g1(j0, npre);
       for (int jj = 1; jj < nl; ++jj) { g1(j0 + jj, 0); g2(j0 + jj - 1); }
       g2(j0 + nl - 1);
+      stamp(0);
       // the X slabs are dead once every first-GEMM MMA has retired: their first half takes this CTA's 64 residual rows
       mbar_wait(x_empty, 0);
+      mbar_expect_tx(xchg_full, (uint32_t)kSlabs * kHSlab);                // the peer's partial: this many bytes will land in [40K, 80K)
+      mbar_arrive_remote(map_to_cta(smem_u32(xchg_ready), peer));          // ... and from now on the peer may send them
       mbar_expect_tx(r_full, (uint32_t)kSlabs * kHSlab);
       for (int kb = 0; kb < kSlabs; ++kb) tma_load_2d(&map_r, r_full, xs + (size_t)kb * kHSlab, kb * 32, tile * BM + (int)rank * HR);
+      stamp(0);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -141,7 +158,9 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     uint32_t act_cnt[2] = {0, 0};
+    stamp(1);
     mbar_wait(x_full, 0);
+    stamp(1);
     tcgen05_fence_after();
     auto g1 = [&](int jj) {   // acc1[jj&1] = X . W1_chunk^T
       const uint32_t d = tmem_base + (uint32_t)((jj & 1) * CH);
@@ -186,8 +205,10 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       }
     };
     g1(0);
-    for (int jj = 1; jj < nl; ++jj) { g1(jj); g2(jj - 1); }
+    stamp(1);
+    for (int jj = 1; jj < nl; ++jj) { g1(jj); stamp(1); g2(jj - 1); stamp(1); }
     g2(nl - 1);
+    stamp(1);
   } else {
     // ===================================================================== activation, partial exchange, final epilogue (warps 2..9)
     const int quad = warp & 3;                       // TMEM lane quadrant (hardware: warp id % 4)
@@ -207,8 +228,11 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       pcache[n1 + 3 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_g[i] : 0.f;
       pcache[n1 + 4 * N2 + i] = p.ep.ln2_g ? p.ep.ln2_b[i] : 0.f;
     }
+    const int role = (warp == 2) ? 2 : (warp == 4 ? 3 : -1);
+    if (role >= 0) stamp(role);
     pdl_wait();   // (the parameter cache above only reads weights)
     epi_bar_sync<256>();
+    if (role >= 0) stamp(role);
     TcParams ep = p.ep;
     ep.bias = pcache + n1;
     ep.ln1_g = pcache + n1 + N2;
@@ -248,17 +272,18 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&act_done[a]);
+      if (role >= 0) stamp(role);
     }
     // ---- this CTA's partial accumulator is complete (so every MMA that read the X slabs has retired)
     mbar_wait(acc2_full, 0);
+    if (role >= 0) stamp(role);
     tcgen05_fence_after();
-    if (warp == 2 && lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(xchg_ready), peer));   // peer may write into my slabs
     const bool owner = ((uint32_t)(quad >> 1) == rank);     // quadrants 0,1 = rows 0..63 (rank 0), quadrants 2,3 = rows 64..127 (rank 1)
     const int trow = (quad & 1) * 32 + lane;                // row inside the 64-row half
     if (!owner) {
-      // ---- ship the peer's 64 rows of my partial accumulator into its exchange tile (same swizzled slab layout as the staging tiles)
-      mbar_wait_cluster(xchg_ready, 0);
-      const uint32_t rbase = map_to_cta(smem_u32(xchg), peer);
+      // ---- stage the peer's 64 rows of my partial accumulator in the idle weight ring (every slab has been consumed: acc2_full),
+      // then ONE thread sends the 40 KB tile into the peer's exchange area with a bulk DSMEM copy
+      uint8_t* ship = ring + (size_t)kSlabs * kHSlab;        // ring [40K, 80K): the first 40 KB stage the second output later
 #pragma unroll 1
       for (int u = cu0; u < cu1; ++u) {
         uint32_t raw[16];
@@ -268,20 +293,28 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int qq = ((u & 1) << 2) | q;
-          const uint32_t off = (uint32_t)(s * kHSlab + trow * 128 + (((qq ^ (trow & 7)) & 7) << 4));
-          st_cluster_v4(rbase + off, __uint_as_float(raw[4 * q + 0]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
-                        __uint_as_float(raw[4 * q + 3]));
+          *reinterpret_cast<float4*>(ship + (size_t)s * kHSlab + (size_t)trow * 128 + (((qq ^ (trow & 7)) & 7) << 4)) =
+              make_float4(__uint_as_float(raw[4 * q + 0]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                          __uint_as_float(raw[4 * q + 3]));
         }
       }
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(xchg_full), peer));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
+      asm volatile("bar.sync 2, 128;" ::: "memory");                 // the four shipping warps
+      if ((quad & 1) == 0 && half == 0 && lane == 0) {
+        mbar_wait_cluster(xchg_ready, 0);
+        if (role >= 0) stamp(role);
+        bulk_copy_to_cta(map_to_cta(smem_u32(xchg), peer), ship, (uint32_t)kSlabs * kHSlab, map_to_cta(smem_u32(xchg_full), peer));
+      }
+      if (role >= 0) stamp(role);
     } else {
       // ---- finish my 64 rows: x = resid + alpha * (mine + peer's + bias2), LayerNorm(s), TMA stores
       mbar_wait(r_full, 0);
-      mbar_wait_cluster(xchg_full, 0);
+      if (role >= 0) stamp(role);
+      mbar_wait(xchg_full, 0);
+      if (role >= 0) stamp(role);
       epilogue_ln_tma<EPI, N2, HR, 2, 128>(ep, tmem_acc2 + lane_addr, xs, &map_c, &map_c2, tile * BM + (int)rank * HR, trow,
                                            (quad & 1) == 0 && half == 0 && lane == 0, half, statbuf, ring, xchg);
+      if (role >= 0) stamp(role);
     }
     tcgen05_fence_before();
   }
@@ -292,6 +325,9 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
+  // the bulk copy reads THIS CTA's ring until the peer has received it (the peer's owners waited on xchg_full before they got
+  // here): neither CTA may retire before both are done
+  cluster_sync_all();
 }
 
 size_t pair_smem() {
@@ -309,7 +345,30 @@ int launch_pair_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1, 
     configured = true;
   }
   (void)ctx;
-  B200_CUDA_OK(launch_k_cluster(kern, dim3(2 * pp.num_m_tiles), dim3(kPairThreads), smem, stream, 2, mx, m1, m2, mr, mc, mc2, pp));
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("B200ASR_PAIR_DBG");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg, sizeof(long long) * 128);
+  }
+  PairParams p2 = pp;
+  p2.dbg = dbg_on ? dbg : nullptr;
+  if (dbg_on) cudaMemset(dbg, 0, sizeof(long long) * 128);
+  B200_CUDA_OK(launch_k_cluster(kern, dim3(2 * pp.num_m_tiles), dim3(kPairThreads), smem, stream, 2, mx, m1, m2, mr, mc, mc2, p2));
+  if (dbg_on) {
+    long long hbuf[128];
+    cudaDeviceSynchronize();
+    cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    long long t0 = 0;
+    for (int i = 0; i < 128; ++i) if (hbuf[i] && (!t0 || hbuf[i] < t0)) t0 = hbuf[i];
+    const char* names[4] = {"producer", "mma", "ship(w2)", "own(w4)"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "pair-dbg %s:", names[r]);
+      for (int i = 0; i < 32 && hbuf[r * 32 + i]; ++i) fprintf(stderr, " %lld", hbuf[r * 32 + i] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
 }
 

@@ -275,7 +275,10 @@ int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorM
   return 1;
 }
 
-int pick_block_n(int N) {
+int pick_block_n(int N, int epilogue, int M, int num_sms) {
+  // QKV projection of ConformerS (N = 432, no epilogue math): two 224-column tiles per 128 rows make one wave of 126 CTAs on
+  // 148 SMs, where three 144-column tiles would need two waves (an MMA costs the same ~132 cycles for N = 144 and N = 224)
+  if (N == 432 && epilogue == EPI_NONE && ceil_div(M, 128) * 3 > num_sms && ceil_div(M, 128) * 2 <= num_sms) return 224;
   if (N % 144 == 0) return 144;
   if (N <= 64) return 64;
   if (N <= 128) return 128;
@@ -332,7 +335,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: tensor-map encoder not initialised");
     return 1;
   }
-  const int bn = (epilogue >= EPI_RESID_LN) ? p.N : pick_block_n(p.N);
+  const int bn = (epilogue >= EPI_RESID_LN) ? p.N : pick_block_n(p.N, epilogue, p.M, ctx.num_sms);
   TcParams tp{};
   tp.bias = p.bias; tp.resid = p.resid; tp.C = p.C; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.ldc = p.ldc; tp.alpha = p.alpha;
   tp.ln1_g = p.ln1_g; tp.ln1_b = p.ln1_b; tp.ln2_g = p.ln2_g; tp.ln2_b = p.ln2_b; tp.C2 = p.C2; tp.ln_eps = p.ln_eps;
@@ -348,7 +351,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   }
   // M tile: 128 rows normally; 64 when 128-row tiles would leave most SMs idle (the 8000-row, N<=256 GEMMs of one batch)
   int bm = 128;
-  if (p.a_mode == 0 && ceil_div(p.M, 128) * tp.num_n_tiles < (ctx.num_sms * 3) / 4) bm = 64;
+  if (p.a_mode == 0 && bn != 224 && ceil_div(p.M, 128) * tp.num_n_tiles < (ctx.num_sms * 3) / 4) bm = 64;
   if (p.a_mode == 0) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 4};
@@ -381,6 +384,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     if (encode_map(ctx, &lnmaps[1], p.C, 2, dims, strides, box, ones)) return 1;
     if (encode_map(ctx, &lnmaps[2], p.C2, 2, dims, strides, box, ones)) return 1;
   }
+  if (bn == 224) return launch_one<EPI_NONE, 224, 128>(ctx, ma, mb, lnmaps, tp, stream);
   if (bm == 64) {
     switch (bn) {
       case 64: return dispatch_epi<64, 64>(ctx, epilogue, ma, mb, lnmaps, tp, stream);

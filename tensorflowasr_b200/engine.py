@@ -288,7 +288,8 @@ class Engine:
             ln2[0].data_ptr() if ln2 else None, ln2[1].data_ptr() if ln2 else None, float(eps), self._stream()), "b200asr_debug_chain")
         return C, C2
 
-    STAGES = {"conv2": 0, "ffn_w1": 1, "ffn_w2": 2, "stft": 3, "sub_linear": 4, "attention": 5, "ctc_fc": 6}
+    STAGES = {"conv2": 0, "ffn_w1": 1, "ffn_w2": 2, "stft": 3, "sub_linear": 4, "attention": 5, "ctc_fc": 6, "ffn_chain": 7,
+              "conv1": 8, "dwconv": 9, "qkv": 10}
 
     def time_stage(self, stage: str, B: int, L: int, iters: int = 20) -> Tuple[float, float, float]:
         """(ms per launch, algorithmic FLOPs per launch, algorithmic HBM bytes per launch) of one kernel timed alone

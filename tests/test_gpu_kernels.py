@@ -1,0 +1,116 @@
+"""GPU kernel-level parity tests (run with -m gpu): every tcgen05 kernel behind the C ABI's test hooks against torch fp64 on the
+same seeded inputs, next to the exact-fp32 CUDA-core kernel of the same operation.
+
+Tolerances: tf32 tensor-core path 2e-2 (plain epilogues) / 3e-2 (LayerNorm epilogues, residual scale 30) / 1e-2 (attention);
+fp32 CUDA-core path 1e-4."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def keng():
+    from tensorflowasr_b200 import engine as E, weights as W
+    ge, re_, gc, rc = W.random_model(0, num_blocks=1)
+    e = E.Engine(ge, re_, gc, rc, precision=0, use_cuda_graph=False)
+    yield e
+    e.close()
+
+
+def _ln(torch, x, g, b, eps=1e-3):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * g + b
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 144, 144), (130, 144, 32), (8000, 576, 144), (8000, 144, 576), (100, 144, 2880), (8000, 1332, 144),
+                                   (300, 256, 256), (8000, 432, 144), (1000, 432, 144), (77, 64, 64), (4097, 128, 96), (1, 144, 144)])
+def test_tcgen05_gemm_epilogues_vs_fp64(keng, torch_mod, M, N, K):
+    """C = epilogue(A W^T): bias / ReLU / swish / GLU / residual / none, tcgen05 tf32 and fp32 CUDA cores (ragged M, N, K tails,
+    the two-tile 224-column QKV configuration at M = 8000, N = 432 included)."""
+    torch = torch_mod
+    torch.manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda")
+    Wt = torch.randn(N, K, device="cuda") / K ** 0.5
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    ref64 = A.double() @ Wt.double().T
+    for epi in (0, 1, 2, 3, 4, 5):
+        if epi == 3 and N % 8:
+            continue
+        r = ref64 + (bias.double() if epi != 5 else 0)
+        if epi == 1:
+            r = r.clamp_min(0)
+        if epi == 2:
+            r = r * torch.sigmoid(r)
+        if epi == 3:
+            r = r[:, 0::2] * torch.sigmoid(r[:, 1::2])
+        if epi == 4:
+            r = resid.double() + 0.5 * r
+        c_tc = keng.debug_gemm(A, Wt, bias, resid, 0.5, epi, True)
+        c_32 = keng.debug_gemm(A, Wt, bias, resid, 0.5, epi, False) if K % 16 == 0 else None
+        torch.cuda.synchronize()
+        assert not torch.isnan(c_tc).any()
+        assert (c_tc.double() - r).abs().max().item() < 2e-2, f"tcgen05 epilogue {epi}"
+        if c_32 is not None:
+            assert (c_32.double() - r).abs().max().item() < 1e-4, f"fp32 epilogue {epi}"
+
+
+@pytest.mark.parametrize("M,N,K", [(8000, 144, 576), (300, 144, 144), (1000, 256, 1024), (129, 64, 128), (8000, 144, 2880)])
+def test_tcgen05_gemm_layernorm_epilogues_vs_fp64(keng, torch_mod, M, N, K):
+    """Residual + LayerNorm (one or two, chained) fused in the GEMM epilogue, in place and out of place."""
+    torch = torch_mod
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda")
+    Wt = torch.randn(N, K, device="cuda") / K ** 0.5
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda") * 30
+    g1, b1, g2, b2 = (torch.randn(N, device="cuda") for _ in range(4))
+    acc = A.double() @ Wt.double().T + bias.double()
+    for epi, inplace in ((6, False), (6, True), (7, False), (7, True), (8, False)):
+        r = resid.clone()
+        x = (r.double() + 0.5 * acc) if epi != 8 else acc
+        if epi == 7:
+            c_ref = _ln(torch, x, g1.double(), b1.double())
+            c2_ref = _ln(torch, c_ref, g2.double(), b2.double())
+        else:
+            c_ref, c2_ref = x, _ln(torch, x, g1.double(), b1.double())
+        C, C2 = keng.debug_gemm_ln(A, Wt, bias, r if epi != 8 else None, 0.5, epi, (g1, b1), (g2, b2) if epi == 7 else None, inplace=inplace)
+        torch.cuda.synchronize()
+        assert not torch.isnan(C2).any()
+        assert (C.double() - c_ref).abs().max().item() < 3e-2
+        assert (C2.double() - c2_ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("B,T,H,dh,wf,wb", [(2, 250, 4, 36, -1, 0), (1, 106, 4, 36, -1, 0), (3, 13, 4, 64, -1, 0), (1, 300, 2, 32, -1, 0),
+                                            (2, 780, 4, 64, -1, 0), (1, 1, 4, 36, -1, 0), (2, 257, 4, 36, -1, 0), (2, 120, 4, 36, 36, 0),
+                                            (1, 300, 4, 36, 36, 8), (32, 250, 4, 36, -1, 0)])
+def test_attention_kernels_vs_fp64(keng, torch_mod, B, T, H, dh, wf, wb):
+    """softmax(Q K^T) V per head (multihead_attention.py:151-188; optional ChunkConformer band, chunk_conformer_blocks.py:158-176):
+    tcgen05 kernel and fp32 CUDA-core kernel against torch fp64, single and multiple key blocks, ragged T."""
+    torch = torch_mod
+    torch.manual_seed(B * 1000 + T)
+    qkv = torch.randn(B * T, 3 * H * dh, device="cuda")
+    qkv[:, :H * dh] *= 0.5
+    q, k, v = (qkv[:, i * H * dh:(i + 1) * H * dh].reshape(B, T, H, dh).double() for i in range(3))
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k)
+    if wf >= 0:
+        i = torch.arange(T, device="cuda")[:, None]
+        j = torch.arange(T, device="cuda")[None, :]
+        lo = torch.clamp(torch.minimum(torch.clamp(i - wf, min=0), torch.tensor(T - wb, device="cuda")), min=0)
+        hi = torch.clamp(torch.maximum(torch.minimum(i + wb, torch.tensor(T, device="cuda")), torch.tensor(wb, device="cuda")), max=T - 1)
+        s = s.masked_fill(~((j >= lo) & (j <= hi)), float("-inf"))
+    ref = torch.einsum("bhnm,bmhd->bnhd", torch.softmax(s, -1), v).reshape(B * T, H * dh)
+    o_tc = keng.debug_attention(qkv, B, T, H, dh, True, wf, wb)
+    o_32 = keng.debug_attention(qkv, B, T, H, dh, False, wf, wb)
+    torch.cuda.synchronize()
+    assert not torch.isnan(o_tc).any()
+    assert (o_tc.double() - ref).abs().max().item() < 1e-2
+    assert (o_32.double() - ref).abs().max().item() < 1e-4
