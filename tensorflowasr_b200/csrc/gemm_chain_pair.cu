@@ -6,7 +6,7 @@
 // rows: CTA r streams the W1 rows / W2 columns of hidden chunks [r*n/2, (r+1)*n/2) only, i.e. half of the MMA instructions, half
 // of the weight bytes through its L2 port and half of the activation work.  The two partial [128 x N2] accumulators are
 // combined through distributed shared memory: each CTA stages the 64 rows it does not own in its (idle) weight ring, swizzled like
-// the staging tiles, and one thread sends them with ONE 40 KB cp.async.bulk.shared::cluster into the peer's dead X slabs
+// the staging tiles, and one warp sends them as five 8 KB cp.async.bulk.shared::cluster copies into the peer's dead X slabs
 // (per-lane st.shared::cluster of row fragments measured 4.7 k cycles for the same bytes); each CTA then finishes residual +
 // LayerNorm(s) + TMA stores for its own 64 rows.
 //
@@ -300,10 +300,13 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
       asm volatile("bar.sync 2, 128;" ::: "memory");                 // the four shipping warps
-      if ((quad & 1) == 0 && half == 0 && lane == 0) {
-        mbar_wait_cluster(xchg_ready, 0);
+      if ((quad & 1) == 0 && half == 0) {                            // one warp: five 8 KB slab copies in flight at once
+        if (lane == 0) mbar_wait_cluster(xchg_ready, 0);
+        __syncwarp();
         if (role >= 0) stamp(role);
-        bulk_copy_to_cta(map_to_cta(smem_u32(xchg), peer), ship, (uint32_t)kSlabs * kHSlab, map_to_cta(smem_u32(xchg_full), peer));
+        if (lane < kSlabs)
+          bulk_copy_to_cta(map_to_cta(smem_u32(xchg + (size_t)lane * kHSlab), peer), ship + (size_t)lane * kHSlab, kHSlab,
+                           map_to_cta(smem_u32(xchg_full), peer));
       }
       if (role >= 0) stamp(role);
     } else {
