@@ -104,6 +104,15 @@ B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B,
 B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host,
                            int32_t* out_len_host, void* stream);
 
+/* Two-deep pipeline over the host-buffer call, for serving loops that keep the GPU busy (the reference's batch decoders use a
+ * thread pool for the same purpose, ctc_beam_search_decoder.cpp:426-459): submit() enqueues H2D of the waveform (pinned host
+ * memory) on a copy stream, the recognise graph and the D2H of ids + lengths on the library's own compute stream and returns at
+ * once; collect() blocks until that slot's results are in the host buffers.  slot is 0 or 1; a slot must be collected before
+ * it is submitted again; the H2D of one slot overlaps the compute of the other.  Host buffers must stay valid until collect(). */
+B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const float* wav_host, int B, int L, int32_t* ids_host,
+                                              int32_t* out_len_host);
+B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot);
+
 /* Roofline instrumentation (bench.py): time one stage of the schedule alone, `iters` launches bracketed by CUDA events on
  * `stream`; also returns that launch's algorithmic FLOPs and HBM bytes.  Run b200asr_recognize with the same (B, L) first. */
 enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 = 2, B200ASR_STAGE_STFT = 3,

@@ -38,6 +38,25 @@ __global__ void __launch_bounds__(256) frame_argmax_kernel(const float* __restri
   if (lane == 0) out[row] = (idx == 0x7fffffff) ? 0 : idx;
 }
 
+// thread per frame: first maximum over the N tiles' partial (max, argmax) pairs (tiles ascend with the class index, so "strictly
+// greater" keeps the lowest class among equals, as ctc_greedy_decoder.h:11-18 does)
+__global__ void __launch_bounds__(256) argmax_combine_kernel(const float2* __restrict__ part, int rows, int n_tiles, int* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  if (row >= rows) return;
+  float best = -INFINITY;
+  int idx = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const float2 v = part[(size_t)row * n_tiles + t];
+    if (v.x > best) {
+      best = v.x;
+      idx = __float_as_int(v.y);
+    }
+  }
+  out[row] = idx;
+}
+
 // warp per utterance: ids[b, :] = collapsed sequence padded with -1, out_len[b] = its length
 __global__ void __launch_bounds__(32) ctc_collapse_kernel(const int* __restrict__ am, const int* __restrict__ lengths,
                                                           int T, int blank, int* __restrict__ ids,
@@ -74,6 +93,15 @@ int launch_ctc_greedy(const float* logits, const int* lengths, int B, int T, int
   if (T > 0) {
     B200_CUDA_OK(launch_k(frame_argmax_kernel, dim3(ceil_div(B * T, 8)), dim3(256), 0, stream, logits, B * T, V, frame_argmax));
   }
+  B200_CUDA_OK(launch_k(ctc_collapse_kernel, dim3(B), dim3(32), 0, stream, (const int*)frame_argmax, lengths, T, blank, ids, out_len));
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_ctc_greedy_partials(const float2* part, int n_tiles, const int* lengths, int B, int T, int blank, int* frame_argmax, int* ids,
+                               int* out_len, cudaStream_t stream) {
+  if (B == 0) return 0;
+  if (T > 0) B200_CUDA_OK(launch_k(argmax_combine_kernel, dim3(ceil_div(B * T, 256)), dim3(256), 0, stream, part, B * T, n_tiles, frame_argmax));
   B200_CUDA_OK(launch_k(ctc_collapse_kernel, dim3(B), dim3(32), 0, stream, (const int*)frame_argmax, lengths, T, blank, ids, out_len));
   B200_CUDA_OK(cudaGetLastError());
   return 0;

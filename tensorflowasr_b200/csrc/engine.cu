@@ -72,6 +72,15 @@ struct b200asr_engine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   TcContext tc;  // tcgen05 GEMM state (tensor-map encoder entry point etc.)
+  // two-deep host pipeline (b200asr_recognize_host_submit / _collect)
+  struct PipeSlot {
+    float* wav = nullptr;
+    int32_t *ids = nullptr, *lens = nullptr;
+    size_t wav_floats = 0, id_ints = 0, len_ints = 0;
+    cudaEvent_t h2d = nullptr, done = nullptr;
+    bool busy = false;
+  } pipe[2];
+  cudaStream_t pipe_copy = nullptr, pipe_compute = nullptr;
 };
 
 namespace {
@@ -176,6 +185,7 @@ struct Buffers {
   float *power, *mel, *c1, *c2, *x, *xn, *h, *att, *g, *logits;
   unsigned int* pmax;
   int *am, *ids, *lens;
+  float2* amp;   // per-(frame, N tile) (max, argmax) partials of the fused CTC head
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -204,6 +214,7 @@ size_t carve(b200asr_handle h, const Shapes& s, Buffers* b, char* base) {
   b->am = reinterpret_cast<int*>(take(M));
   b->ids = reinterpret_cast<int*>(take(M));
   b->lens = reinterpret_cast<int*>(take(s.B));
+  b->amp = reinterpret_cast<float2*>(take(M * 2 * (size_t)(std::max(c.vocab, 1) / 64 + 2)));
   return off;
 }
 
@@ -419,6 +430,13 @@ int run_ctc(Ctx& c, const float* enc, int B, int Tp, const Buffers& b, float* lo
     for (size_t i = 0; i < h->ctc_blocks.size(); ++i) {
       const LNW* next = (i + 1 < h->ctc_blocks.size()) ? &h->ctc_blocks[i + 1].ffn1.ln : nullptr;
       if (run_block_fused(c, h->ctc_blocks[i], bb, B, Tp, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps, next)) return 1;
+    }
+    if (logits == nullptr) {
+      // greedy path: the CTC head keeps only per-tile (max, argmax) pairs (EPI_BIAS_ARGMAX); no logits are written
+      GemmParams fp{};
+      fp.A = bb.x; fp.W = h->ctc_fcw; fp.bias = h->ctc_fcb; fp.C = reinterpret_cast<float*>(b.amp); fp.M = M; fp.N = cfg.vocab; fp.K = D;
+      fp.lda = D; fp.ldc = cfg.vocab;
+      return gemm_p(c, fp, EPI_BIAS_ARGMAX);
     }
     return gemm(c, bb.x, D, h->ctc_fcw, h->ctc_fcb, nullptr, 0.f, logits, cfg.vocab, M, cfg.vocab, D, EPI_BIAS);
   }
@@ -667,6 +685,15 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   if (h->mel_wc) cudaFree(h->mel_wc);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->beam_ws) cudaFree(h->beam_ws);
+  for (auto& ps : h->pipe) {
+    if (ps.wav) cudaFree(ps.wav);
+    if (ps.ids) cudaFree(ps.ids);
+    if (ps.lens) cudaFree(ps.lens);
+    if (ps.h2d) cudaEventDestroy(ps.h2d);
+    if (ps.done) cudaEventDestroy(ps.done);
+  }
+  if (h->pipe_copy) cudaStreamDestroy(h->pipe_copy);
+  if (h->pipe_compute) cudaStreamDestroy(h->pipe_compute);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -803,9 +830,21 @@ B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B,
     Ctx c{h, st};
     ENG_TRY(h, run_encoder(c, wav_dev, s, b));
     // the CTC decoder sees whole utterances: [B0, Tp, D]; its input is the encoder output held in b.x
-    ENG_TRY(h, run_ctc(c, b.x, B0, Tp, b, b.logits));
+    // tensor-core path: CTC head fused with the per-frame argmax (no 42.6 MB logits round trip at the benchmark shape)
+    GemmParams probe{};
+    probe.A = b.x; probe.W = h->ctc_fcw; probe.bias = h->ctc_fcb; probe.C = reinterpret_cast<float*>(b.amp); probe.M = s.M;
+    probe.N = h->cfg.vocab; probe.K = h->cfg.dmodel; probe.lda = h->cfg.dmodel; probe.ldc = h->cfg.vocab;
+    const bool fused_argmax = h->cfg.precision == B200ASR_PRECISION_TF32 && fused_ln_ok(h) && !h->ctc_blocks.empty() &&
+                              tc_gemm_supported(probe, EPI_BIAS_ARGMAX) && h->cfg.vocab / 64 + 2 >= tc_argmax_tiles(h->cfg.vocab);
     h->launches += 2;
-    ENG_TRY(h, launch_ctc_greedy(b.logits, nullptr, B0, Tp, h->cfg.vocab, h->cfg.vocab - 1, b.am, ids_dev, out_len_dev, st));
+    if (fused_argmax) {
+      ENG_TRY(h, run_ctc(c, b.x, B0, Tp, b, nullptr));
+      ENG_TRY(h, launch_ctc_greedy_partials(b.amp, tc_argmax_tiles(h->cfg.vocab), nullptr, B0, Tp, h->cfg.vocab - 1, b.am, ids_dev,
+                                            out_len_dev, st));
+    } else {
+      ENG_TRY(h, run_ctc(c, b.x, B0, Tp, b, b.logits));
+      ENG_TRY(h, launch_ctc_greedy(b.logits, nullptr, B0, Tp, h->cfg.vocab, h->cfg.vocab - 1, b.am, ids_dev, out_len_dev, st));
+    }
     return 0;
   });
 }
@@ -834,6 +873,69 @@ B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, 
   ENG_CUDA(h, cudaMemcpyAsync(ids_host, b.ids, sizeof(int32_t) * (size_t)B * Tp, cudaMemcpyDeviceToHost, st));
   ENG_CUDA(h, cudaMemcpyAsync(out_len_host, b.lens, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   ENG_CUDA(h, cudaStreamSynchronize(st));
+  return 0;
+}
+
+B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const float* wav_host, int B, int L, int32_t* ids_host,
+                                  int32_t* out_len_host) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 1 || B <= 0 || L <= 0 || !wav_host || !ids_host || !out_len_host)
+    return fail(h, "b200asr_recognize_host_submit: bad arguments");
+  if (h->cfg.vocab <= 0) return fail(h, "b200asr_recognize_host_submit: engine was created without a CTC decoder");
+  auto& ps = h->pipe[slot];
+  if (ps.busy) return fail(h, "b200asr_recognize_host_submit: slot still in flight (collect it first)");
+  if (!h->pipe_copy) {
+    ENG_CUDA(h, cudaStreamCreateWithFlags(&h->pipe_copy, cudaStreamNonBlocking));
+    ENG_CUDA(h, cudaStreamCreateWithFlags(&h->pipe_compute, cudaStreamNonBlocking));
+  }
+  if (!ps.h2d) {
+    ENG_CUDA(h, cudaEventCreateWithFlags(&ps.h2d, cudaEventDisableTiming));
+    ENG_CUDA(h, cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+  }
+  int Be = B, Le = L;
+  effective_batch(h, &Be, &Le);
+  const Shapes s = shapes_for(h, Be, Le);
+  const int Tp = s.M / B;
+  const size_t nw = (size_t)B * L, ni = (size_t)B * Tp;
+  // staging buffers live outside the workspace: the other slot's graph may be running on it while this slot's waveform lands
+  if (nw > ps.wav_floats) {
+    if (ps.wav) ENG_CUDA(h, cudaFree(ps.wav));
+    ps.wav = nullptr; ps.wav_floats = 0;
+    ENG_CUDA(h, cudaMalloc(&ps.wav, nw * sizeof(float)));
+    ps.wav_floats = nw;
+  }
+  if (ni > ps.id_ints) {
+    if (ps.ids) ENG_CUDA(h, cudaFree(ps.ids));
+    ps.ids = nullptr; ps.id_ints = 0;
+    ENG_CUDA(h, cudaMalloc(&ps.ids, ni * sizeof(int32_t)));
+    ps.id_ints = ni;
+  }
+  if ((size_t)B > ps.len_ints) {
+    if (ps.lens) ENG_CUDA(h, cudaFree(ps.lens));
+    ps.lens = nullptr; ps.len_ints = 0;
+    ENG_CUDA(h, cudaMalloc(&ps.lens, (size_t)B * sizeof(int32_t)));
+    ps.len_ints = (size_t)B;
+  }
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;     // (may synchronise the device when it has to grow: only before the first submit)
+  ENG_CUDA(h, cudaMemcpyAsync(ps.wav, wav_host, nw * sizeof(float), cudaMemcpyHostToDevice, h->pipe_copy));
+  ENG_CUDA(h, cudaEventRecord(ps.h2d, h->pipe_copy));
+  ENG_CUDA(h, cudaStreamWaitEvent(h->pipe_compute, ps.h2d, 0));
+  if (b200asr_recognize(h, ps.wav, B, L, ps.ids, ps.lens, h->pipe_compute)) return 1;
+  ENG_CUDA(h, cudaMemcpyAsync(ids_host, ps.ids, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, h->pipe_compute));
+  ENG_CUDA(h, cudaMemcpyAsync(out_len_host, ps.lens, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->pipe_compute));
+  ENG_CUDA(h, cudaEventRecord(ps.done, h->pipe_compute));
+  ps.busy = true;
+  return 0;
+}
+
+B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 1) return fail(h, "b200asr_recognize_host_collect: bad slot");
+  auto& ps = h->pipe[slot];
+  if (!ps.busy) return fail(h, "b200asr_recognize_host_collect: nothing was submitted on this slot");
+  ENG_CUDA(h, cudaEventSynchronize(ps.done));
+  ps.busy = false;
   return 0;
 }
 

@@ -215,6 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         epilogue_ln_tma<EPI, BLOCK_N, BLOCK_M>(p, taddr, stile, &map_c, &map_c2, mt * BLOCK_M, trow, warp == 2 && lane == 0);
         __syncwarp();
         if (kHasResidTile && lane == 0) mbar_arrive(r_empty);
+      } else if constexpr (EPI == EPI_BIAS_ARGMAX) {
+        epilogue_argmax<BLOCK_N>(p, taddr, grow0, nrows, nt * BLOCK_N, nt, lane);
       } else {
         epilogue_plain<EPI, BLOCK_N>(p, taddr, wsm, grow0, nrows, nt * BLOCK_N, lane);
       }
@@ -235,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ------------------------------------------------------------------------------------------------ host side
 template <int EPI, int BLOCK_N, int BLOCK_M>
 constexpr size_t smem_bytes() {
-  constexpr bool is_ln = (EPI >= EPI_RESID_LN);
+  constexpr bool is_ln = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2 || EPI == EPI_BIAS_LN);
   return (size_t)stages_for(is_ln, BLOCK_N, BLOCK_M) * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4) +
          (is_ln ? (size_t)BLOCK_M * ((BLOCK_N + 31) / 32) * 128 : (size_t)4 * kWsmFloats * 4 /*epilogue transpose scratch*/) +
          1024 /*align slack*/ + 256 /*barriers*/;
@@ -270,6 +272,9 @@ int dispatch_epi(TcContext& ctx, int epi, const CUtensorMap& ma, const CUtensorM
     case EPI_RESID_LN: return launch_one<EPI_RESID_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
     case EPI_RESID_LN2: return launch_one<EPI_RESID_LN2, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
     case EPI_BIAS_LN: return launch_one<EPI_BIAS_LN, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+    case EPI_BIAS_ARGMAX:
+      if constexpr (BLOCK_M == 128) return launch_one<EPI_BIAS_ARGMAX, BLOCK_N, BLOCK_M>(ctx, ma, mb, lnmaps, tp, s);
+      break;
   }
   snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: bad epilogue %d", epi);
   return 1;
@@ -317,10 +322,13 @@ int tc_init(TcContext* ctx) {
   return 0;
 }
 
+int tc_argmax_tiles(int N) { return ceil_div(N, pick_block_n(N, EPI_BIAS_ARGMAX, 1, 148)); }
+
 bool tc_gemm_supported(const GemmParams& p, int epilogue) {
   if (p.M <= 0 || p.N % 4 != 0 || p.K % 4 != 0) return false;
   if (epilogue == EPI_GLU && p.N % 8 != 0) return false;
-  if (epilogue >= EPI_RESID_LN) {
+  if (epilogue == EPI_BIAS_ARGMAX && (p.a_mode != 0 || p.bias == nullptr)) return false;
+  if (epi_is_ln(epilogue)) {
     // fused LayerNorm: the row must be exactly one instantiated tile width, plain A operand, bias present
     if (p.a_mode != 0 || p.bias == nullptr || p.C2 == nullptr || p.ln1_g == nullptr || p.N != p.ldc) return false;
     if (!(p.N == 64 || p.N == 128 || p.N == 144 || p.N == 192 || p.N == 256)) return false;
@@ -335,7 +343,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: tensor-map encoder not initialised");
     return 1;
   }
-  const int bn = (epilogue >= EPI_RESID_LN) ? p.N : pick_block_n(p.N, epilogue, p.M, ctx.num_sms);
+  const int bn = epi_is_ln(epilogue) ? p.N : pick_block_n(p.N, epilogue, p.M, ctx.num_sms);
   TcParams tp{};
   tp.bias = p.bias; tp.resid = p.resid; tp.C = p.C; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.ldc = p.ldc; tp.alpha = p.alpha;
   tp.ln1_g = p.ln1_g; tp.ln1_b = p.ln1_b; tp.ln2_g = p.ln2_g; tp.ln2_b = p.ln2_b; tp.C2 = p.C2; tp.ln_eps = p.ln_eps;
@@ -351,7 +359,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   }
   // M tile: 128 rows normally; 64 when 128-row tiles would leave most SMs idle (the 8000-row, N<=256 GEMMs of one batch)
   int bm = 128;
-  if (p.a_mode == 0 && bn != 224 && ceil_div(p.M, 128) * tp.num_n_tiles < (ctx.num_sms * 3) / 4) bm = 64;
+  if (p.a_mode == 0 && bn != 224 && epilogue != EPI_BIAS_ARGMAX && ceil_div(p.M, 128) * tp.num_n_tiles < (ctx.num_sms * 3) / 4) bm = 64;
   if (p.a_mode == 0) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 4};
@@ -376,7 +384,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   // LayerNorm epilogues: residual-in / output tiles travel by TMA ([M, N] in BLOCK_M x 32-column slabs; stores clip tails)
   CUtensorMap lnmaps[3];
   memset(lnmaps, 0, sizeof(lnmaps));
-  if (epilogue >= EPI_RESID_LN) {
+  if (epi_is_ln(epilogue)) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
     const cuuint64_t strides[1] = {(cuuint64_t)p.ldc * 4};
     const cuuint32_t box[2] = {32, (cuuint32_t)bm};

@@ -45,7 +45,11 @@ enum Epilogue : int {
   EPI_RESID_LN = 6,    // x = resid + alpha*(acc+bias) -> C;  LN(x; ln1) -> C2
   EPI_RESID_LN2 = 7,   // y = LN(resid + alpha*(acc+bias); ln1) -> C;  LN(y; ln2) -> C2 (skipped when ln2_g == null)
   EPI_BIAS_LN = 8,     // x = acc + bias -> C;  LN(x; ln1) -> C2
+  // CTC head fused with the greedy decoder's per-frame argmax (tcgen05 path only): no logits are stored;
+  // C = float2 [M, ceil(N / BLOCK_N)] holding (max, bit pattern of the first arg max) of acc + bias over each N tile
+  EPI_BIAS_ARGMAX = 9,
 };
+inline bool epi_is_ln(int e) { return e == EPI_RESID_LN || e == EPI_RESID_LN2 || e == EPI_BIAS_LN; }
 
 struct GemmParams {
   const float* A;      // [M, K] row-major (lda), or conv2 source [B, T1, F1, D] when a_mode == 1
@@ -93,6 +97,11 @@ int launch_dwconv(const DwConvParams& p, cudaStream_t stream);
 // argmax over V per frame (first maximum wins, as ctc_greedy_decoder.h:11-18), then merge repeats / drop blank.
 int launch_ctc_greedy(const float* logits, const int* lengths /*nullable*/, int B, int T, int V, int blank,
                       int* frame_argmax /*[B*T] scratch*/, int* ids /*[B, T]*/, int* out_len /*[B]*/, cudaStream_t stream);
+// the same from per-tile (max, argmax) partials written by the EPI_BIAS_ARGMAX GEMM epilogue: part [B*T, n_tiles] float2
+int launch_ctc_greedy_partials(const float2* part, int n_tiles, const int* lengths /*nullable*/, int B, int T, int blank,
+                               int* frame_argmax, int* ids, int* out_len, cudaStream_t stream);
+// number of N tiles the tcgen05 GEMM uses for an N-column EPI_BIAS_ARGMAX launch (gemm_tc.cu)
+int tc_argmax_tiles(int N);
 
 struct BeamParams {
   const float* logits;   // [B, T, V] (pre-softmax) -- softmax is applied inside, as the callers of ctc_beam_search_decoder do

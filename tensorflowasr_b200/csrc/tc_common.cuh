@@ -252,6 +252,35 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, uint32_t taddr
   }
 }
 
+// CTC head + per-frame argmax: the thread (== output row) keeps the running first maximum of acc + bias over this tile's valid
+// columns and writes one (max, argmax) pair per (row, N tile); the logits never leave the SM.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_argmax(const TcParams& p, uint32_t taddr, size_t grow0, int nrows, int gcol0, int nt, int lane) {
+  float best = -INFINITY;
+  int bidx = 0;
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 16) {
+    if (gcol0 + c >= p.N) break;                     // warp-uniform
+    uint32_t raw[16];
+    tmem_ld16_nowait(taddr + (uint32_t)c, raw);      // warp-collective
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = gcol0 + c + 4 * q;
+      if (col < p.N) {                               // N % 4 == 0: the four columns are valid together
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        const float v0 = __uint_as_float(raw[4 * q + 0]) + b.x, v1 = __uint_as_float(raw[4 * q + 1]) + b.y;
+        const float v2 = __uint_as_float(raw[4 * q + 2]) + b.z, v3 = __uint_as_float(raw[4 * q + 3]) + b.w;
+        if (v0 > best) { best = v0; bidx = col; }
+        if (v1 > best) { best = v1; bidx = col + 1; }
+        if (v2 > best) { best = v2; bidx = col + 2; }
+        if (v3 > best) { best = v3; bidx = col + 3; }
+      }
+    }
+  }
+  if (lane < nrows) reinterpret_cast<float2*>(p.C)[(grow0 + lane) * (size_t)p.num_n_tiles + nt] = make_float2(best, __int_as_float(bidx));
+}
+
 // ------------------------------------------------------------------------------------------------ fused LayerNorm epilogues
 // thread == output row and BLOCK_N == N, so a row's statistics never leave the thread: the accumulator row is swept from
 // TMEM two (three) times -- statistics (shifted one-pass variance), then normalise -- instead of being parked in registers.

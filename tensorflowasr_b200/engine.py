@@ -61,6 +61,8 @@ def load_library() -> ctypes.CDLL:
         lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
     lib.b200asr_recognize.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.b200asr_recognize_host_submit.argtypes = [vp, ci, vp, ci, ci, vp, vp]
+    lib.b200asr_recognize_host_collect.argtypes = [vp, ci]
     lib.b200asr_time_stage.argtypes = [vp, ci, ci, ci, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_double)]
     lib.b200asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, vp]
@@ -298,6 +300,16 @@ class Engine:
         self._check(self.lib.b200asr_time_stage(self._h, self.STAGES[stage], int(B), int(L), int(iters), self._stream(),
                                                 ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by)), "b200asr_time_stage")
         return float(ms.value), float(fl.value), float(by.value)
+
+    def recognize_host_submit(self, slot, wav_host, ids_host, lens_host):
+        """Two-deep pipeline (b200asr_recognize_host_submit): pinned torch CPU tensors in / out, returns at once."""
+        B, L = wav_host.shape
+        self._check(self.lib.b200asr_recognize_host_submit(self._h, int(slot), wav_host.data_ptr(), B, L, ids_host.data_ptr(),
+                                                           lens_host.data_ptr()), "b200asr_recognize_host_submit")
+
+    def recognize_host_collect(self, slot):
+        """Blocks until the slot's ids / lengths are in the host buffers given to recognize_host_submit."""
+        self._check(self.lib.b200asr_recognize_host_collect(self._h, int(slot)), "b200asr_recognize_host_collect")
 
     def recognize_host(self, wav_host, ids_host=None, lens_host=None):
         """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Synchronises."""

@@ -328,3 +328,59 @@ def test_chained_ffn_kernels_vs_fp64(eng32, torch_mod, pair, M, N1):
         assert not torch.isnan(C2).any()
         assert (C.double() - c_ref).abs().max().item() < 3e-2
         assert (C2.double() - c2_ref).abs().max().item() < 3e-2
+
+
+def test_host_pipeline_matches_synchronous_call(eng, ref_wav, torch_mod):
+    """b200asr_recognize_host_submit / _collect (two slots, H2D of one batch under the compute of the other) returns exactly
+    what the synchronous host call returns, for alternating inputs and re-used slots."""
+    torch = torch_mod
+    L = 24000
+    rng = np.random.default_rng(11)
+    batches = []
+    for i in range(5):
+        x = np.clip(rng.standard_normal((3, L)).astype(np.float32) * 0.1, -1, 1)
+        x[i % 3] = np.tile(ref_wav, 2)[i * 1000:i * 1000 + L]
+        batches.append(torch.from_numpy(x).pin_memory())
+    want = []
+    for xb in batches:
+        ids, lens = eng.recognize_host(xb)
+        want.append((ids.clone(), lens.clone()))
+    Tp = want[0][0].shape[1]
+    hid = [torch.empty((3, Tp), dtype=torch.int32).pin_memory() for _ in range(2)]
+    hlen = [torch.empty((3,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    got = [None] * len(batches)
+    for i, xb in enumerate(batches):
+        sl = i & 1
+        if i >= 2:
+            eng.recognize_host_collect(sl)
+            got[i - 2] = (hid[sl].clone(), hlen[sl].clone())
+        eng.recognize_host_submit(sl, xb, hid[sl], hlen[sl])
+    for i in range(len(batches) - 2, len(batches)):
+        eng.recognize_host_collect(i & 1)
+        got[i] = (hid[i & 1].clone(), hlen[i & 1].clone())
+    for (wi, wl), (gi, gl) in zip(want, got):
+        assert torch.equal(wl, gl)
+        for b in range(3):
+            n = int(wl[b])
+            assert torch.equal(wi[b, :n], gi[b, :n])
+    with pytest.raises(RuntimeError):
+        eng.recognize_host_collect(0)          # nothing in flight any more
+
+
+def test_fused_argmax_head_equals_logits_path(eng, ref_wav, torch_mod):
+    """recognize() (tf32: CTC head fused with the per-frame argmax, no logits materialised) returns exactly the ids obtained by
+    collapsing the argmax of the logits the same engine writes through b200asr_ctc_logits -- the reference's greedy rule
+    (first maximum wins, ctc_greedy_decoder.h:11-18) on identical arithmetic."""
+    from oracle import ctc_ref
+    L = 40000
+    rng = np.random.default_rng(5)
+    x = np.clip(rng.standard_normal((6, L)).astype(np.float32) * 0.1, -1, 1)
+    x[1] = np.tile(ref_wav, 2)[:L]
+    x[4] = np.tile(ref_wav, 2)[3000:3000 + L]
+    ids, lens = eng.recognize(x)
+    logits = eng.ctc_logits(eng.encode(x)).cpu().numpy()
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    for b in range(x.shape[0]):
+        want = ctc_ref.greedy_decode(logits[b], logits.shape[-1] - 1)
+        assert ids[b, :lens[b]].tolist() == want
+    assert lens[1] > 5 and lens[4] > 5
