@@ -147,7 +147,8 @@ B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const floa
                                     const float* ln2_b, float eps, void* stream);
 
 /* Same contract as b200asr_debug_chain through the cluster-pair variant (hidden dimension split across two CTAs, partial
- * accumulators exchanged through distributed shared memory); N2 = 144, N1 = 288 or 576 only. */
+ * accumulators exchanged through distributed shared memory); N2 = 144, N1 = 288 or 576 only.  N1 = 0 (W1 = b1 = NULL, K1 = 144)
+ * selects the DIRECT mode: C/C2 = LN-epilogue(resid + alpha * (X . W2^T + b2)) with K split across the pair. */
 B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const float* W1, const float* b1, const float* W2,
                                          const float* b2, const float* resid, float* C, float* C2, int M, int K1, int N1, int N2,
                                          float alpha, int epilogue, const float* ln1_g, const float* ln1_b, const float* ln2_g,

@@ -162,12 +162,13 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   bool kv_loaded = false;
 
   // staging helpers: 4 independent 16-byte loads in flight per thread before the first shared-memory store
-  auto stage_rows = [&](uint8_t* dst, const float* src, int row0, int rows) {   // row-major tile -> K-major SW128 (Q, K)
-    for (int i0 = tid; i0 < rows * (kDP / 4); i0 += 4 * kThreadsA) {
+  // (t0, nt): the staging threads are t0 .. t0 + nt - 1 of the CTA (all of it, or the four warps that idle during the softmax)
+  auto stage_rows = [&](uint8_t* dst, const float* src, int row0, int rows, int t0 = 0, int nt = kThreadsA) {   // row-major tile -> K-major SW128 (Q, K)
+    for (int i0 = tid - t0; i0 < rows * (kDP / 4); i0 += 4 * nt) {
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kThreadsA;
+        const int i = i0 + u * nt;
         const int r = i >> 4, c4 = i & 15;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < rows * (kDP / 4) && row0 + r < p.T && 4 * c4 < dh)
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kThreadsA;
+        const int i = i0 + u * nt;
         if (i < rows * (kDP / 4)) {
           const int r = i >> 4, c4 = i & 15;
           float4 w = v[u];
@@ -210,9 +211,11 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     }
   };
 
+  bool q_staged = false;                          // the next query tile was staged under the previous tile's softmax
   for (int q0 = blockIdx.x * kQT; q0 < p.T; q0 += gridDim.x * kQT) {
   stamp();
-  stage_rows(Qs, qbase, q0, kQT);               // rows beyond T and columns beyond dh are zero
+  if (!q_staged) stage_rows(Qs, qbase, q0, kQT);  // rows beyond T and columns beyond dh are zero
+  q_staged = false;
   stamp();
 
   // per-row state: warps 0..7, row = (warp & 3) * 32 + lane; `half` selects this thread's 128 key columns of a block and
@@ -261,6 +264,16 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     stamp();
     phase ^= 1;
     fence_after();
+    // ---- the Q tile is dead once the last S = Q K^T of this query tile has completed: the four warps that do not take part in
+    // the softmax stage the NEXT query tile over it now (visible to the tensor core through the proxy fence + the barriers below)
+    const int q_next = q0 + gridDim.x * kQT;
+    if (k0 + kKT >= p.T && q_next < p.T) {
+      if (warp >= 8) {
+        stage_rows(Qs, qbase, q_next, kQT, 256, kThreadsA - 256);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      q_staged = true;
+    }
     // ---- softmax over this block's keys (8 warps: each thread sweeps its 128 columns twice), P written back in place
     float corr = 1.f;
     const int nk = min(kKT, p.T - k0);

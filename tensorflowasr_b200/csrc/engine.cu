@@ -283,7 +283,19 @@ int gemm_resid_ln(Ctx& c, const float* A, int K, const float* W, const float* bi
   p.A = A; p.W = W; p.bias = bias; p.resid = b.x; p.C = b.x; p.C2 = b.xn; p.M = M; p.N = D; p.K = K; p.lda = K; p.ldc = D;
   p.alpha = alpha; p.ln1_g = ln1.g; p.ln1_b = ln1.b; p.ln_eps = eps;
   if (ln2) { p.ln2_g = ln2->g; p.ln2_b = ln2->b; }
-  return gemm_p(c, p, ln2 ? EPI_RESID_LN2 : EPI_RESID_LN);
+  const int epi = ln2 ? EPI_RESID_LN2 : EPI_RESID_LN;
+  if (c.h->use_chain && c.h->use_pair && c.h->cfg.precision == B200ASR_PRECISION_TF32 && c.h->tc.ready) {
+    // 144 -> 144 projections (attention output): cluster-pair kernel with K split across the pair
+    ChainGemmParams cp{};
+    cp.X = A; cp.W2 = W; cp.bias2 = bias; cp.resid = b.x; cp.C = b.x; cp.C2 = b.xn; cp.M = M; cp.K1 = K; cp.N1 = 0; cp.N2 = D; cp.ldx = K;
+    cp.alpha = alpha; cp.ln1_g = ln1.g; cp.ln1_b = ln1.b; cp.ln_eps = eps;
+    if (ln2) { cp.ln2_g = ln2->g; cp.ln2_b = ln2->b; }
+    if (tc_pair_direct_supported(cp, epi)) {
+      c.h->launches++;
+      return launch_gemm_chain_pair(c.h->tc, cp, epi, c.s);
+    }
+  }
+  return gemm_p(c, p, epi);
 }
 
 // x = x + alpha * (swish(X.W1^T + b1).W2^T + b2) with the LayerNorm epilogue(s), as ONE chained kernel when supported,
@@ -1135,7 +1147,8 @@ B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const
   ChainGemmParams cp{};
   cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;
   cp.N2 = N2; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1_g; cp.ln1_b = ln1_b; cp.ln2_g = ln2_g; cp.ln2_b = ln2_b; cp.ln_eps = eps;
-  if (!tc_chain_pair_supported(cp, epilogue)) return fail(h, "b200asr_debug_chain_pair: shape not supported by the cluster-pair kernel");
+  if (N1 == 0 ? !tc_pair_direct_supported(cp, epilogue) : !tc_chain_pair_supported(cp, epilogue))
+    return fail(h, "b200asr_debug_chain_pair: shape not supported by the cluster-pair kernel");
   h->launches++;
   ENG_TRY(h, launch_gemm_chain_pair(h->tc, cp, epilogue, static_cast<cudaStream_t>(stream)));
   return 0;

@@ -13,6 +13,9 @@
 //   warp 0      TMA producer (first weight slabs before griddepcontrol.wait; X; weight ring; the 64-row residual tile)
 //   warp 1      MMA issuer + TMEM owner (acc1 double buffer [0,2CH), partial acc2 [2CH, 2CH+N2))
 //   warps 2-9   activation of every local chunk; then quadrants of the peer's rows ship, quadrants of the own rows finish
+// DIRECT variant (attention out-projection): no hidden layer -- acc2 = X . W2^T with the K dimension (144 = 18 k-steps) split 9 / 9
+// across the pair, then the same exchange and residual + LayerNorm epilogue (64 rows per CTA on 8 warps instead of the plain
+// GEMM kernel's 64-row tiles whose epilogue runs on 4 half-empty warps).
 // Cross-CTA protocol (mbarriers, one tile per CTA, so every parity is 0):
 //   xchg_ready  (in the WRITER's smem, arrived remotely by the destination's producer as soon as its first-GEMM MMAs have
 //               retired): "my X slabs are dead, you may write into them"
@@ -46,7 +49,7 @@ struct PairParams {
   long long* dbg;    // optional timeline of cluster 0 / CTA 0 (B200ASR_PAIR_DBG=1): [role][event] clock64 stamps
 };
 
-template <int EPI>
+template <int EPI, bool DIRECT>
 __global__ void __launch_bounds__(kPairThreads, 1)
 gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                        const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_r,
@@ -133,15 +136,22 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       auto g2 = [&](int j) { for (int kb = 0; kb < KB2; ++kb) ring_load(&map_w2, j * CH + kb * 32, 0, N2 * 128); };
       // weights are constants: the first slabs are requested before griddepcontrol.wait (under the previous kernel's tail)
       const int npre = p.kb1 < STAGES ? p.kb1 : STAGES;
-      for (int kb = 0; kb < npre; ++kb) ring_load(&map_w1, kb * 32, j0 * CH, CH * 128);
+      if (DIRECT) {
+        // this CTA's half of K: k-steps [9 rank, 9 rank + 9) live in weight slabs {0,1,2} (rank 0) / {2,3,4} (rank 1)
+        for (int i = 0; i < 3; ++i) ring_load(&map_w2, (2 * (int)rank + i) * 32, 0, N2 * 128);
+      } else {
+        for (int kb = 0; kb < npre; ++kb) ring_load(&map_w1, kb * 32, j0 * CH, CH * 128);
+      }
       stamp(0);
       pdl_wait();
       stamp(0);
       mbar_expect_tx(x_full, (uint32_t)p.kb1 * kXSlab);
       for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d(&map_x, x_full, xs + (size_t)kb * kXSlab, kb * 32, tile * BM);
-      g1(j0, npre);
-      for (int jj = 1; jj < nl; ++jj) { g1(j0 + jj, 0); g2(j0 + jj - 1); }
-      g2(j0 + nl - 1);
+      if (!DIRECT) {
+        g1(j0, npre);
+        for (int jj = 1; jj < nl; ++jj) { g1(j0 + jj, 0); g2(j0 + jj - 1); }
+        g2(j0 + nl - 1);
+      }
       stamp(0);
       // the X slabs are dead once every first-GEMM MMA has retired: their first half takes this CTA's 64 residual rows
       mbar_wait(x_empty, 0);
@@ -204,11 +214,41 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     };
-    g1(0);
-    stamp(1);
-    for (int jj = 1; jj < nl; ++jj) { g1(jj); stamp(1); g2(jj - 1); stamp(1); }
-    g2(nl - 1);
-    stamp(1);
+    if constexpr (DIRECT) {
+      // acc2 = X[:, my K half] . W2[:, my K half]^T : global k-steps [9 rank, 9 rank + 9), four per 32-column slab
+      const int ks0 = 9 * (int)rank, ks1 = ks0 + 9;
+      bool first = true;
+      for (int i = 0; i < 3; ++i) {
+        const int kb = 2 * (int)rank + i;                    // slab of X and of the weights
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_smem_desc(smem_u32(xs + (size_t)kb * kXSlab));
+          const uint64_t db = make_smem_desc(smem_u32(ring + (size_t)stage * kRing));
+          for (int k = 0; k < 4; ++k) {
+            const int step = 4 * kb + k;
+            if (step >= ks0 && step < ks1) {
+              umma_tf32(tmem_acc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, first ? 0u : 1u);
+              first = false;
+            }
+          }
+          tcgen05_commit(&empty_bar[stage]);
+          if (i == 2) {
+            tcgen05_commit(acc2_full);
+            tcgen05_commit(x_empty);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      stamp(1);
+    } else {
+      g1(0);
+      stamp(1);
+      for (int jj = 1; jj < nl; ++jj) { g1(jj); stamp(1); g2(jj - 1); stamp(1); }
+      g2(nl - 1);
+      stamp(1);
+    }
   } else {
     // ===================================================================== activation, partial exchange, final epilogue (warps 2..9)
     const int quad = warp & 3;                       // TMEM lane quadrant (hardware: warp id % 4)
@@ -220,7 +260,8 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint32_t full_cnt[2] = {0, 0};
     const int n1 = nl * CH;
     const int et = threadIdx.x - 64;                   // 0..255 among these warps
-    for (int i = et; i < n1; i += 256) pcache[i] = p.bias1[j0 * CH + i];
+    if (!DIRECT)
+      for (int i = et; i < n1; i += 256) pcache[i] = p.bias1[j0 * CH + i];
     for (int i = et; i < N2; i += 256) {
       pcache[n1 + i] = p.ep.bias[i];
       pcache[n1 + N2 + i] = p.ep.ln1_g[i];
@@ -337,10 +378,10 @@ size_t pair_smem() {
   return (size_t)kSlabs * kXSlab + (size_t)STAGES * kRing + 1024 + 256 + HR * 2 * 4 * 4 + (2 * CH + 5 * N2) * 4 + 64;
 }
 
-template <int EPI>
+template <int EPI, bool DIRECT>
 int launch_pair_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mr,
                   const CUtensorMap& mc, const CUtensorMap& mc2, const PairParams& pp, cudaStream_t stream) {
-  auto kern = gemm_chain_pair_kernel<EPI>;
+  auto kern = gemm_chain_pair_kernel<EPI, DIRECT>;
   const size_t smem = pair_smem();
   static bool configured = false;
   if (!configured) {
@@ -384,6 +425,15 @@ bool tc_chain_pair_supported(const ChainGemmParams& p, int epilogue) {
   return p.N1 % CH == 0 && nch >= 2 && nch % 2 == 0 && nch / 2 <= 2;   // pcache holds at most 2 local chunks of bias1
 }
 
+// DIRECT mode: ChainGemmParams with N1 == 0 and W1 == bias1 == null means C/C2 = LN-epilogue(resid + alpha * (X . W2^T + bias2)),
+// X [M, 144], W2 [144, 144] (the attention out-projection with its residual + LayerNorm)
+bool tc_pair_direct_supported(const ChainGemmParams& p, int epilogue) {
+  if (epilogue != EPI_RESID_LN && epilogue != EPI_RESID_LN2) return false;
+  if (p.N1 != 0 || p.N2 != N2 || p.K1 != N2 || p.ldx != p.K1 || p.M <= 0) return false;
+  if (!p.bias2 || !p.resid || !p.C || !p.C2 || !p.ln1_g || !p.X || !p.W2) return false;
+  return ((reinterpret_cast<uintptr_t>(p.X) | reinterpret_cast<uintptr_t>(p.W2)) & 15) == 0;
+}
+
 int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream) {
   if (!ctx.ready) {
     snprintf(g_errbuf, sizeof(g_errbuf), "gemm_chain_pair: tensor-map encoder not initialised");
@@ -394,7 +444,8 @@ int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogu
   pp.ep.ldc = p.N2; pp.ep.alpha = p.alpha; pp.ep.ln1_g = p.ln1_g; pp.ep.ln1_b = p.ln1_b; pp.ep.ln2_g = p.ln2_g; pp.ep.ln2_b = p.ln2_b;
   pp.ep.ln_eps = p.ln_eps;
   pp.bias1 = p.bias1;
-  pp.nl = p.N1 / CH / 2;
+  const bool direct = (p.N1 == 0);
+  pp.nl = direct ? 0 : p.N1 / CH / 2;
   pp.kb1 = ceil_div(p.K1, 32);
   pp.num_m_tiles = ceil_div(p.M, BM);
   const cuuint32_t ones[2] = {1, 1};
@@ -406,16 +457,19 @@ int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogu
     if (encode_map(ctx, &mx, p.X, 2, dims, strides, box, ones)) return 1;
   }
   {
+    const int kw2 = direct ? p.K1 : p.N1;                    // K extent of the second operand
+    const cuuint64_t dims[2] = {(cuuint64_t)kw2, (cuuint64_t)p.N2};
+    const cuuint64_t strides[1] = {(cuuint64_t)kw2 * 4};
+    const cuuint32_t box[2] = {32, N2};
+    if (encode_map(ctx, &m2, p.W2, 2, dims, strides, box, ones)) return 1;
+  }
+  if (direct) {
+    m1 = m2;                                                 // (not used by the DIRECT kernel)
+  } else {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K1, (cuuint64_t)p.N1};
     const cuuint64_t strides[1] = {(cuuint64_t)p.K1 * 4};
     const cuuint32_t box[2] = {32, CH};
     if (encode_map(ctx, &m1, p.W1, 2, dims, strides, box, ones)) return 1;
-  }
-  {
-    const cuuint64_t dims[2] = {(cuuint64_t)p.N1, (cuuint64_t)p.N2};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.N1 * 4};
-    const cuuint32_t box[2] = {32, N2};
-    if (encode_map(ctx, &m2, p.W2, 2, dims, strides, box, ones)) return 1;
   }
   {
     // residual in / outputs: [M, N2] in tiles of 64 rows x 32-column slabs (stores clip the M and column tails)
@@ -426,8 +480,12 @@ int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogu
     if (encode_map(ctx, &mc, p.C, 2, dims, strides, box, ones)) return 1;
     if (encode_map(ctx, &mc2, p.C2, 2, dims, strides, box, ones)) return 1;
   }
-  if (epilogue == EPI_RESID_LN) return launch_pair_t<EPI_RESID_LN>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
-  return launch_pair_t<EPI_RESID_LN2>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
+  if (direct) {
+    if (epilogue == EPI_RESID_LN) return launch_pair_t<EPI_RESID_LN, true>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
+    return launch_pair_t<EPI_RESID_LN2, true>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
+  }
+  if (epilogue == EPI_RESID_LN) return launch_pair_t<EPI_RESID_LN, false>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
+  return launch_pair_t<EPI_RESID_LN2, false>(ctx, mx, m1, m2, mr, mc, mc2, pp, stream);
 }
 
 }  // namespace b200asr

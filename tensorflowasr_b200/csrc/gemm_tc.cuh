@@ -28,6 +28,8 @@ bool tc_chain_supported(const ChainGemmParams& p, int epilogue);
 int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);
 // same result with the hidden dimension split across a cluster of two CTAs (gemm_chain_pair.cu)
 bool tc_chain_pair_supported(const ChainGemmParams& p, int epilogue);
+// N1 == 0: no hidden layer, C/C2 = LN-epilogue(resid + alpha * (X . W2^T + bias2)) with K split across the pair
+bool tc_pair_direct_supported(const ChainGemmParams& p, int epilogue);
 int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);
 
 }  // namespace b200asr

@@ -276,6 +276,19 @@ class Engine:
                                                      int(win_back), int(bool(tensor_cores)), self._stream()), "b200asr_debug_attention")
         return out
 
+    def debug_pair_direct(self, X, W, bias, resid, alpha, epilogue, ln1, ln2=None, eps=1e-3):
+        """Test hook: 144 -> 144 projection + residual + LayerNorm through the cluster-pair kernel (K split across the pair)."""
+        torch = _torch()
+        M, K = X.shape
+        N = W.shape[0]
+        C = torch.empty((M, N), device=self._dev(), dtype=torch.float32)
+        C2 = torch.zeros((M, N), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_debug_chain_pair(
+            self._h, X.data_ptr(), None, None, W.data_ptr(), bias.data_ptr(), resid.data_ptr(), C.data_ptr(), C2.data_ptr(), M, K, 0, N,
+            float(alpha), int(epilogue), ln1[0].data_ptr(), ln1[1].data_ptr(), ln2[0].data_ptr() if ln2 else None,
+            ln2[1].data_ptr() if ln2 else None, float(eps), self._stream()), "b200asr_debug_chain_pair")
+        return C, C2
+
     def debug_chain(self, X, W1, b1, W2, b2, resid, alpha, epilogue, ln1, ln2=None, eps=1e-3, inplace=True, pair=False):
         """Test hook: chained FFN-style kernel (pair=True: the 2-CTA-cluster variant).  Returns (C, C2)."""
         torch = _torch()

@@ -114,3 +114,29 @@ def test_attention_kernels_vs_fp64(keng, torch_mod, B, T, H, dh, wf, wb):
     assert not torch.isnan(o_tc).any()
     assert (o_tc.double() - ref).abs().max().item() < 1e-2
     assert (o_32.double() - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("M", [8000, 300, 1, 129, 8064])
+def test_pair_direct_projection_vs_fp64(keng, torch_mod, M):
+    """Attention out-projection + residual + LayerNorm on the cluster-pair kernel (K = 144 split 72 / 72 across the two CTAs,
+    partial sums exchanged through DSMEM) against torch fp64."""
+    torch = torch_mod
+    torch.manual_seed(M)
+    D = 144
+    X = torch.randn(M, D, device="cuda")
+    W = torch.randn(D, D, device="cuda") / D ** 0.5
+    bias = torch.randn(D, device="cuda") * 0.3
+    g1, b1, g2, b2 = (torch.randn(D, device="cuda") for _ in range(4))
+    resid = torch.randn(M, D, device="cuda") * 20
+    x = resid.double() + 1.0 * (X.double() @ W.double().T + bias.double())
+    for epi in (6, 7):
+        if epi == 6:
+            c_ref, c2_ref = x, _ln(torch, x, g1.double(), b1.double())
+        else:
+            c_ref = _ln(torch, x, g1.double(), b1.double())
+            c2_ref = _ln(torch, c_ref, g2.double(), b2.double())
+        C, C2 = keng.debug_pair_direct(X, W, bias, resid, 1.0, epi, (g1, b1), (g2, b2) if epi == 7 else None)
+        torch.cuda.synchronize()
+        assert not torch.isnan(C2).any()
+        assert (C.double() - c_ref).abs().max().item() < 3e-2
+        assert (C2.double() - c2_ref).abs().max().item() < 3e-2

@@ -384,3 +384,56 @@ def test_fused_argmax_head_equals_logits_path(eng, ref_wav, torch_mod):
         want = ctc_ref.greedy_decode(logits[b], logits.shape[-1] - 1)
         assert ids[b, :lens[b]].tolist() == want
     assert lens[1] > 5 and lens[4] > 5
+
+
+def test_config5_full_size_beam16_properties(eng, ref_wav, torch_mod):
+    """BASELINE config 5 shape (ConformerCTC(S) + prefix beam 16, batch 128 x 5 s): size-independent properties -- hypotheses
+    sorted by score, beam 1 == greedy on every row, tiled-speech rows all return the same 16 hypotheses, best beam hypothesis ==
+    greedy ids where the greedy path is unambiguous (speech rows)."""
+    L, B = 80000, 128
+    speech = np.tile(ref_wav, 2)[:L]
+    rng = np.random.default_rng(1237)
+    x = np.clip(rng.standard_normal((B, L)).astype(np.float32) * 0.1, -1, 1)
+    x[::8] = speech
+    xs = torch_mod.from_numpy(x).cuda()
+    gids, glens = eng.recognize(xs)
+    logits = eng.ctc_logits(eng.encode(xs))
+    ids, lens, scores = eng.ctc_beam(logits, 16)
+    i1, l1, _ = eng.ctc_beam(logits, 1)
+    gids, glens, ids, lens, scores = (t.cpu().numpy() for t in (gids, glens, ids, lens, scores))
+    i1, l1 = i1.cpu().numpy(), l1.cpu().numpy()
+    assert np.isfinite(scores[lens >= 0]).all()
+    for b in range(B):
+        n = int((lens[b] >= 0).sum())
+        assert n >= 1 and (np.diff(scores[b, :n]) <= 1e-6).all()                       # descending scores
+        assert i1[b, 0, :l1[b, 0]].tolist() == gids[b, :glens[b]].tolist()             # beam 1 == greedy
+    for b in range(0, B, 8):
+        assert (lens[b] == lens[0]).all()                                              # identical rows, identical beams
+        for k in range(16):
+            if lens[0, k] >= 0:
+                assert (ids[b, k, :lens[b, k]] == ids[0, k, :lens[0, k]]).all()
+        assert ids[b, 0, :lens[b, 0]].tolist() == gids[b, :glens[b]].tolist()
+    assert glens[0] >= 13                                                               # >= one pass of the 13-token utterance
+
+
+def test_config3_full_size_streaming_properties(streaming_weights, ref_wav, torch_mod):
+    """BASELINE config 3 shape (StreamingConformerCTC, batch 64 x 30 s = 3840 independent 8000-sample chunks, global CTC
+    decoder over 780 frames): finite, identical rows decode identically, and a row equals the same utterance run alone."""
+    from tensorflowasr_b200 import engine as E
+    ge, re_, gc, rc = streaming_weights
+    e = E.Engine(ge, re_, gc, rc, precision=0, chunk_samples=8000)
+    L, B = 480000, 64
+    speech = np.tile(ref_wav, 8)[:L]
+    rng = np.random.default_rng(1235)
+    x = np.clip(rng.standard_normal((B, L)).astype(np.float32) * 0.1, -1, 1)
+    x[::16] = speech
+    xs = torch_mod.from_numpy(x).cuda()
+    ids, lens = e.recognize(xs)
+    enc = e.encode(xs)
+    assert tuple(enc.shape) == (64, 780, 256) and torch_mod.isfinite(enc).all()
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    one_ids, one_len = e.recognize(speech[None])
+    for r in range(0, B, 16):
+        assert lens[r] == int(one_len[0]) and (ids[r, :lens[r]] == one_ids[0, :lens[r]].cpu().numpy()).all()
+    assert lens[0] >= 60
+    e.close()
