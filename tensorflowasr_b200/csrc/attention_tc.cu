@@ -161,13 +161,15 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   const bool single_block = (p.T <= kKT);       // K / V^T staged once and reused by every query tile of this CTA
   bool kv_loaded = false;
 
-  // staging helpers: 4 independent 16-byte loads in flight per thread before the first shared-memory store
+  // staging helpers: kSU independent 16-byte loads in flight per thread before the first shared-memory store (the staging loops
+  // are bound by global-load latency: measured 6.4 k cycles for K + V^T with 4 in flight)
+  constexpr int kSU = 8;
   // (t0, nt): the staging threads are t0 .. t0 + nt - 1 of the CTA (all of it, or the four warps that idle during the softmax)
   auto stage_rows = [&](uint8_t* dst, const float* src, int row0, int rows, int t0 = 0, int nt = kThreadsA) {   // row-major tile -> K-major SW128 (Q, K)
-    for (int i0 = tid - t0; i0 < rows * (kDP / 4); i0 += 4 * nt) {
-      float4 v[4];
+    for (int i0 = tid - t0; i0 < rows * (kDP / 4); i0 += kSU * nt) {
+      float4 v[kSU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kSU; ++u) {
         const int i = i0 + u * nt;
         const int r = i >> 4, c4 = i & 15;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
           v[u] = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + 4 * c4);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kSU; ++u) {
         const int i = i0 + u * nt;
         if (i < rows * (kDP / 4)) {
           const int r = i >> 4, c4 = i & 15;
@@ -187,10 +189,10 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     }
   };
   auto stage_vt = [&](int k0) {                                                 // V [key][d] -> V^T [d][key] K-major SW128
-    for (int i0 = tid; i0 < kKT * (kDP / 4); i0 += 4 * kThreadsA) {
-      float4 v[4];
+    for (int i0 = tid; i0 < kKT * (kDP / 4); i0 += kSU * kThreadsA) {
+      float4 v[kSU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kSU; ++u) {
         const int i = i0 + u * kThreadsA;
         const int key = i & (kKT - 1), c4 = i >> 8;   // key fastest: conflict-free transposed stores
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
           v[u] = *reinterpret_cast<const float4*>(vbase + (size_t)(k0 + key) * ld + 4 * c4);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kSU; ++u) {
         const int i = i0 + u * kThreadsA;
         if (i < kKT * (kDP / 4)) {
           const int key = i & (kKT - 1), c4 = i >> 8;

@@ -512,12 +512,15 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 b = *reinterpret_cast<const float4*>(p.bias + 16 * u + 4 * q);   // (may point to shared memory)
-      float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
-      float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
+      float a0 = __uint_as_float(raw[4 * q + 0]), a1 = __uint_as_float(raw[4 * q + 1]);
+      float a2 = __uint_as_float(raw[4 * q + 2]), a3 = __uint_as_float(raw[4 * q + 3]);
       if (xchg != nullptr) {
+        // the two partial sums are added FIRST (a commutative step), the bias after: a row's result must not depend on which CTA
+        // of the pair finishes it, i.e. on the utterance's position in the batch
         const float4 o = *chunk_ptr_in(xchg, u, q);
         a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
       }
+      a0 += b.x; a1 += b.y; a2 += b.z; a3 += b.w;
       if (has_resid) {
         const float4 r = *chunk_ptr(u, q);
         a0 = r.x + p.alpha * a0; a1 = r.y + p.alpha * a1; a2 = r.z + p.alpha * a2; a3 = r.w + p.alpha * a3;
