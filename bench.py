@@ -239,7 +239,7 @@ def main():
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
-        for i in range(args.warmup):
+        for i in range(max(args.warmup, NROT)):     # at least one pass over every rotated input: each has its own captured CUDA graph
             step(i)
         barrier()
         sampler = ClockSampler(local_rank)

@@ -161,9 +161,10 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   const bool single_block = (p.T <= kKT);       // K / V^T staged once and reused by every query tile of this CTA
   bool kv_loaded = false;
 
-  // staging helpers: kSU independent 16-byte loads in flight per thread before the first shared-memory store (the staging loops
-  // are bound by global-load latency: measured 6.4 k cycles for K + V^T with 4 in flight)
-  constexpr int kSU = 8;
+  // staging helpers: kSU independent 16-byte loads in flight per thread before the first shared-memory store (measured: 8 in
+  // flight made the kernel slower, 20.7 vs 18.6 us; pre-zeroed padding with fewer stores did not help either -- the loops are
+  // bound by the latency of the strided global loads)
+  constexpr int kSU = 4;
   // (t0, nt): the staging threads are t0 .. t0 + nt - 1 of the CTA (all of it, or the four warps that idle during the softmax)
   auto stage_rows = [&](uint8_t* dst, const float* src, int row0, int rows, int t0 = 0, int nt = kThreadsA) {   // row-major tile -> K-major SW128 (Q, K)
     for (int i0 = tid - t0; i0 < rows * (kDP / 4); i0 += kSU * nt) {
