@@ -202,8 +202,19 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not precede the JSON line on stdout
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version (and, with NCCL_DEBUG=INFO, much more) on stdout while the communicator comes up; stdout must
+        # carry only the JSON line, so file descriptor 1 points at stderr until the first collective has completed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     md = ort_ref.model_dir("offline")
     if md is not None:
@@ -283,8 +294,52 @@ def main():
         e2e_s = e2e_sync_s
         # the same through the two-deep pipeline of the C ABI (b200asr_recognize_host_submit / _collect): every step still
         # copies its own 20.5 MB waveform batch from pinned host memory and reads its ids back, but the H2D of step i+1 overlaps
-        # the compute of step i.  (N > 1 keeps the synchronous loop: the ids all_gather runs on torch's stream.)
+        # the compute of step i.  (N > 1 builds the same overlap from the Python API, see below.)
         e2e_mode = "synchronous b200asr_recognize_host call per step"
+        if world > 1:
+            # N > 1: the same two-deep overlap built from the Python API (Engine.recognize on device buffers + NCCL all_gather of the
+            # ids): a copy stream brings step i+1's waveforms from pinned host memory into the other device buffer while step i
+            # computes; every step still moves its own 20.5 MB in and its gathered ids out
+            copy_stream = torch.cuda.Stream()
+            dev_in2 = [torch.empty_like(dev[0]) for _ in range(2)]
+            hid2 = [hid, torch.empty_like(hid).pin_memory()]
+            hlen2 = [hlen, torch.empty_like(hlen).pin_memory()]
+            h2d_done = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            done = [torch.cuda.Event() for _ in range(2)]
+            for ev in consumed:
+                ev.record(stream)
+
+            def submit(i, base):
+                sl = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[sl])              # the compute that last read this buffer has finished
+                    dev_in2[sl].copy_(host[(base + i) % NROT], non_blocking=True)
+                    h2d_done[sl].record(copy_stream)
+                stream.wait_event(h2d_done[sl])
+                eng.recognize(dev_in2[sl], ids, lens)
+                consumed[sl].record(stream)
+                dist.all_gather(gather_ids, ids)
+                dist.all_gather(gather_lens, lens)
+                hid2[sl].copy_(gather_ids[rank], non_blocking=True)
+                hlen2[sl].copy_(gather_lens[rank], non_blocking=True)
+                done[sl].record(stream)
+
+            def pipelined_n(n, base):
+                for i in range(n):
+                    if i >= 2:
+                        done[i & 1].synchronize()
+                    submit(i, base)
+                for i in range(max(n - 2, 0), n):
+                    done[i & 1].synchronize()
+
+            pipelined_n(max(args.warmup, 2), 0)
+            barrier()
+            t0 = time.perf_counter()
+            pipelined_n(args.steps, 3)
+            barrier()
+            e2e_s = time.perf_counter() - t0
+            e2e_mode = "two-deep pipeline (copy stream + Engine.recognize + NCCL all_gather of ids): H2D of step i+1 under the compute of step i"
         if world == 1:
             hid2 = [hid, torch.empty_like(hid).pin_memory()]
             hlen2 = [hlen, torch.empty_like(hlen).pin_memory()]
