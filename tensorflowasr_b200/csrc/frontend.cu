@@ -233,25 +233,28 @@ __global__ void __launch_bounds__(256) db_mel_fast_kernel(const float* __restric
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
   const float maxlg = (mode == 0) ? log2_floor(__uint_as_float(pmax[b])) : 0.0f;
-  constexpr int NIT = (FR * kBins + 255) / 256;
-  float pv[NIT];
+  // frame-major / bin-minor: bin k = tid + 256 j (j = 0, 1, 2) of every frame, so no index needs a division (the first version
+  // spent most of its 34 M warp instructions on i / 513 and 64-bit address arithmetic); all FR * 3 loads are issued before use
+  constexpr int NJ = (kBins + 255) / 256;
+  float pv[FR][NJ];
+  const float* prow = power + ((size_t)b * T + t0) * ps + tid;
 #pragma unroll
-  for (int j = 0; j < NIT; ++j) {
-    const int i = tid + 256 * j;
-    const int f = i / kBins, k = i - f * kBins;
-    pv[j] = (i < FR * kBins && t0 + f < T) ? __ldg(power + ((size_t)b * T + t0 + f) * ps + k) : 1.0f;
-  }
+  for (int f = 0; f < FR; ++f)
 #pragma unroll
-  for (int j = 0; j < NIT; ++j) {
-    const int i = tid + 256 * j;
-    const int f = i / kBins, k = i - f * kBins;
-    if (i < FR * kBins) {
-      float vdb;
-      if (mode == 0) vdb = fmaxf(3.0102999566398120f * (log2_floor(pv[j]) - maxlg), -80.0f);
-      else vdb = 0.30102999566398120f * log2_floor(pv[j]);
-      db[f][k] = vdb;
+    for (int j = 0; j < NJ; ++j)
+      pv[f][j] = (tid + 256 * j < kBins && t0 + f < T) ? __ldg(prow + (size_t)f * ps + 256 * j) : 1.0f;
+#pragma unroll
+  for (int f = 0; f < FR; ++f)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = tid + 256 * j;
+      if (k < kBins) {
+        float vdb;
+        if (mode == 0) vdb = fmaxf(3.0102999566398120f * (log2_floor(pv[f][j]) - maxlg), -80.0f);
+        else vdb = 0.30102999566398120f * log2_floor(pv[f][j]);
+        db[f][k] = vdb;
+      }
     }
-  }
   __syncthreads();
   for (int o = tid; o < FR * n_mels; o += 256) {
     const int f = o / n_mels, m = o - f * n_mels;
@@ -259,7 +262,8 @@ __global__ void __launch_bounds__(256) db_mel_fast_kernel(const float* __restric
     if (t >= T) continue;
     const int lo = lo_s[m], w0 = off_s[m], n = off_s[m + 1] - w0;
     float acc = 0.0f;
-    for (int k = 0; k < n; ++k) acc = fmaf(db[f][lo + k], wc_s[w0 + k], acc);
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) acc = fmaf(db[f][lo + k], wc_s[w0 + k], acc);   // (same summation order as the reference's dot product)
     mel[((size_t)b * T + t) * n_mels + m] = acc;
   }
 }
