@@ -402,11 +402,8 @@ bool attention_tc_supported(const AttnParams& p) {
 int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
   if (p.B == 0 || p.T == 0) return 0;
   const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + 8 * kDP * 128 + 1024 + 64 + 2 * 128 * 2 * 4;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static PerDeviceSmem configured;
+  if (configured.need(smem)) B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one CTA per (batch, head) when the whole sequence is a single key block (K / V^T staged once for all query tiles)
   const int qtiles = ceil_div(p.T, kQT);
   dim3 grid(p.T <= kKT ? 1 : qtiles, p.H, p.B);

@@ -265,14 +265,13 @@ int launch_attention(const AttnParams& p, cudaStream_t stream) {
   const size_t smem = sizeof(float) * (size_t)(3 * 64 * dhs + 64 * 68);
   dim3 grid(ceil_div(p.T, kAttQ), p.H, p.B);
   const int cpt = ceil_div(p.dh, 16);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceSmem configured;
+  if (configured.need(1)) {
     const int big = (int)(sizeof(float) * (3 * 64 * 68 + 64 * 68));
     B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200_CUDA_OK(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    configured = true;
   }
   switch (cpt) {
     case 1: B200_CUDA_OK(launch_k(attention_kernel<1>, grid, dim3(256), smem, stream, p, dhs)); break;

@@ -35,6 +35,20 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 extern bool g_pdl_enabled;   // engine.cu; B200ASR_NO_PDL=1 in the environment turns the launch attribute off
 
+// cudaFuncSetAttribute (dynamic shared memory size) is per DEVICE: a kernel's launcher keeps one of these per instantiation and
+// sets the attribute once for every device an engine is created on (several engines on different GPUs may live in one process)
+struct PerDeviceSmem {
+  size_t set[64] = {};
+  // true when the attribute must be (re)applied for `bytes` on the current device
+  bool need(size_t bytes) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (set[d] >= bytes && bytes > 0) return false;
+    set[d] = bytes;
+    return true;
+  }
+};
+
 // cluster_x > 1: thread-block cluster of that many CTAs along x (grid.x must be a multiple of it)
 template <class... KArgs, class... Args>
 inline cudaError_t launch_k_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,

@@ -85,6 +85,18 @@ struct b200asr_engine {
 
 namespace {
 
+// every entry point runs on the engine's device whatever the caller's current device is, and puts the caller's device back
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 int fail(b200asr_handle h, const char* msg) {
   if (h) h->err = msg;
   snprintf(g_errbuf, sizeof(g_errbuf), "%s", msg);
@@ -722,6 +734,7 @@ B200ASR_API int b200asr_out_frames(b200asr_handle h, int num_samples) {
 
 B200ASR_API int b200asr_reserve(b200asr_handle h, int B, int L) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B <= 0 || L <= 0) return fail(h, "b200asr_reserve: B and L must be positive");
   effective_batch(h, &B, &L);
   Buffers b;
@@ -733,6 +746,7 @@ B200ASR_API int64_t b200asr_launch_count(b200asr_handle h) { return h ? h->launc
 
 B200ASR_API int b200asr_mel(b200asr_handle h, const float* wav_dev, int B, int L, float* mel_dev, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B < 0 || L <= 0 || !wav_dev || !mel_dev) return fail(h, "b200asr_mel: bad arguments");
   if (B == 0) return 0;
   effective_batch(h, &B, &L);
@@ -746,6 +760,7 @@ B200ASR_API int b200asr_mel(b200asr_handle h, const float* wav_dev, int B, int L
 
 B200ASR_API int b200asr_encode(b200asr_handle h, const float* wav_dev, int B, int L, float* enc_dev, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B < 0 || L <= 0 || !wav_dev || !enc_dev) return fail(h, "b200asr_encode: bad arguments");
   if (B == 0) return 0;
   effective_batch(h, &B, &L);
@@ -765,6 +780,7 @@ B200ASR_API int b200asr_encode(b200asr_handle h, const float* wav_dev, int B, in
 
 B200ASR_API int b200asr_ctc_logits(b200asr_handle h, const float* enc_dev, int B, int Tp, float* logits_dev, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (h->cfg.vocab <= 0) return fail(h, "b200asr_ctc_logits: engine was created without a CTC decoder");
   if (B < 0 || Tp < 0 || !enc_dev || !logits_dev) return fail(h, "b200asr_ctc_logits: bad arguments");
   if (B == 0 || Tp == 0) return 0;
@@ -786,6 +802,7 @@ B200ASR_API int b200asr_ctc_logits(b200asr_handle h, const float* enc_dev, int B
 B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank,
                        int32_t* ids_dev, int32_t* out_len_dev, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B < 0 || Tp < 0 || V <= 0 || !ids_dev || !out_len_dev || (!logits_dev && B * Tp > 0))
     return fail(h, "b200asr_ctc_greedy: bad arguments");
   if (B == 0) return 0;
@@ -802,6 +819,7 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
                      int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev,
                      void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B < 0 || Tp < 0 || V <= 0 || !ids_dev || !out_len_dev || !scores_dev || (!logits_dev && B * Tp > 0))
     return fail(h, "b200asr_ctc_beam: bad arguments");
   if (B == 0) return 0;
@@ -826,6 +844,7 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
 B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev, int32_t* out_len_dev,
                       void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (h->cfg.vocab <= 0) return fail(h, "b200asr_recognize: engine was created without a CTC decoder");
   if (B < 0 || L <= 0 || !wav_dev || !ids_dev || !out_len_dev) return fail(h, "b200asr_recognize: bad arguments");
   if (B == 0) return 0;
@@ -864,6 +883,7 @@ B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B,
 B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host, int32_t* out_len_host,
                            void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B < 0 || L <= 0 || !wav_host || !ids_host || !out_len_host) return fail(h, "b200asr_recognize_host: bad arguments");
   if (B == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -891,6 +911,7 @@ B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, 
 B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const float* wav_host, int B, int L, int32_t* ids_host,
                                   int32_t* out_len_host) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (slot < 0 || slot > 1 || B <= 0 || L <= 0 || !wav_host || !ids_host || !out_len_host)
     return fail(h, "b200asr_recognize_host_submit: bad arguments");
   if (h->cfg.vocab <= 0) return fail(h, "b200asr_recognize_host_submit: engine was created without a CTC decoder");
@@ -943,6 +964,7 @@ B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const 
 
 B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (slot < 0 || slot > 1) return fail(h, "b200asr_recognize_host_collect: bad slot");
   auto& ps = h->pipe[slot];
   if (!ps.busy) return fail(h, "b200asr_recognize_host_collect: nothing was submitted on this slot");
@@ -957,6 +979,7 @@ B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot) {
 B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, int iters, void* stream, float* ms_per_launch,
                        double* flops, double* bytes) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   if (B <= 0 || L <= 0 || iters <= 0 || !ms_per_launch || !flops || !bytes) return fail(h, "b200asr_time_stage: bad arguments");
   effective_batch(h, &B, &L);
   Shapes s = shapes_for(h, B, L);
@@ -1082,6 +1105,7 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
 B200ASR_API int b200asr_debug_gemm(b200asr_handle h, const float* A, const float* W, const float* bias, const float* resid, float* C,
                        int M, int N, int K, int lda, int ldc, float alpha, int epilogue, int use_tensor_cores, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   GemmParams p{};
   p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.alpha = alpha;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1100,6 +1124,7 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
                           float* C2, int M, int N, int K, float alpha, int epilogue, const float* ln1_g, const float* ln1_b,
                           const float* ln2_g, const float* ln2_b, float eps, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   GemmParams p{};
   p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C; p.C2 = C2; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N;
   p.alpha = alpha; p.ln1_g = ln1_g; p.ln1_b = ln1_b; p.ln2_g = ln2_g; p.ln2_b = ln2_b; p.ln_eps = eps;
@@ -1113,6 +1138,7 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
 B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, float* out, int B, int T, int H, int dh, int win_front,
                             int win_back, int use_tensor_cores, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   AttnParams ap{};
   ap.qkv = qkv; ap.out = out; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = win_front; ap.win_back = win_back;
   h->launches++;
@@ -1130,6 +1156,7 @@ B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const floa
                         const float* resid, float* C, float* C2, int M, int K1, int N1, int N2, float alpha, int epilogue,
                         const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   ChainGemmParams cp{};
   cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;
   cp.N2 = N2; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1_g; cp.ln1_b = ln1_b; cp.ln2_g = ln2_g; cp.ln2_b = ln2_b; cp.ln_eps = eps;
@@ -1144,6 +1171,7 @@ B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const
                              const float* resid, float* C, float* C2, int M, int K1, int N1, int N2, float alpha, int epilogue,
                              const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream) {
   if (!h) return 1;
+  DeviceGuard dev_guard(h->device);
   ChainGemmParams cp{};
   cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;
   cp.N2 = N2; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1_g; cp.ln1_b = ln1_b; cp.ln2_g = ln2_g; cp.ln2_b = ln2_b; cp.ln_eps = eps;

@@ -278,11 +278,8 @@ int launch_frontend(const FrontendParams& p, cudaStream_t stream) {
   dim3 g1(ceil_div(p.T, 2), p.B);
   if (!legacy) {
     const size_t smem = sizeof(float2) * kNfft + sizeof(float) * kNfft + sizeof(float2) * kSwTile * kSwWarps;
-    static bool configured = false;
-    if (!configured) {
-      B200_CUDA_OK(cudaFuncSetAttribute(stft_power_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
+    static PerDeviceSmem configured;
+    if (configured.need(smem)) B200_CUDA_OK(cudaFuncSetAttribute(stft_power_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 gw(ceil_div(ceil_div(p.T, 2), kSwWarps * kSwPairs), p.B);
     B200_CUDA_OK(launch_k(stft_power_warp_kernel, gw, dim3(kSwWarps * 32), smem, stream, p.wav, p.window, p.twiddle, p.power, p.pmax, p.L, p.T,
                           p.pad_left, p.hop, p.power_stride));

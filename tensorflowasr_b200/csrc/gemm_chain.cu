@@ -315,11 +315,8 @@ int launch_chain_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1,
                    const CUtensorMap& mc, const CUtensorMap& mc2, const ChainParams& cp, cudaStream_t stream) {
   auto kern = gemm_chain_kernel<EPI, CH, N2, STAGES>;
   const size_t smem = chain_smem<CH, N2, STAGES>(cp.kb1);
-  static size_t configured = 0;
-  if (smem > configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static PerDeviceSmem configured;
+  if (configured.need(smem)) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = cp.num_m_tiles < ctx.num_sms ? cp.num_m_tiles : ctx.num_sms;
   static long long* dbg = nullptr;
   static int dbg_on = -1;

@@ -383,11 +383,8 @@ int launch_pair_t(TcContext& ctx, const CUtensorMap& mx, const CUtensorMap& m1, 
                   const CUtensorMap& mc, const CUtensorMap& mc2, const PairParams& pp, cudaStream_t stream) {
   auto kern = gemm_chain_pair_kernel<EPI, DIRECT>;
   const size_t smem = pair_smem();
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static PerDeviceSmem configured;
+  if (configured.need(smem)) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   (void)ctx;
   static long long* dbg = nullptr;
   static int dbg_on = -1;

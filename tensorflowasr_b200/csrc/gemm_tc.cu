@@ -246,12 +246,10 @@ constexpr size_t smem_bytes() {
 template <int EPI, int BLOCK_N, int BLOCK_M>
 int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* lnmaps, const TcParams& tp,
                cudaStream_t stream) {
-  static bool configured = false;
+  static PerDeviceSmem configured;
   auto kern = gemm_tc_kernel<EPI, BLOCK_N, BLOCK_M>;
-  if (!configured) {
+  if (configured.need(smem_bytes<EPI, BLOCK_N, BLOCK_M>()))
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<EPI, BLOCK_N, BLOCK_M>()));
-    configured = true;
-  }
   const int tiles = tp.num_m_tiles * tp.num_n_tiles;
   const int grid = tiles < ctx.num_sms ? tiles : ctx.num_sms;
   B200_CUDA_OK(launch_k(kern, dim3(grid), dim3(kThreads), smem_bytes<EPI, BLOCK_N, BLOCK_M>(), stream, ma, mb, lnmaps[0], lnmaps[1], lnmaps[2], tp));
