@@ -240,6 +240,40 @@ __global__ void __launch_bounds__(512) dwconv_reg_kernel(const DwConvParams p) {
   }
 }
 
+// Two channels per thread with packed fp32x2 FMAs (bit-identical to the scalar kernel: two independent round-to-nearest FMAs):
+// half the instructions, 8-byte coalesced rows.  D must be even.
+__device__ __forceinline__ unsigned long long dw_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  return c;
+}
+template <int K, int TT>
+__global__ void __launch_bounds__(256) dwconv_reg2_kernel(const DwConvParams p) {
+  pdl_trigger();
+  const int c = 2 * threadIdx.x;
+  if (c >= p.D) return;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TT;
+  const float* xb = p.x + (size_t)b * p.T * p.D + c;
+  unsigned long long w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = *reinterpret_cast<const unsigned long long*>(p.w + j * p.D + c);   // taps are weights
+  pdl_wait();
+  unsigned long long in[TT + K - 1];
+#pragma unroll
+  for (int i = 0; i < TT + K - 1; ++i) {
+    const int tt = t0 + i - p.pad_left;
+    in[i] = (tt >= 0 && tt < p.T) ? *reinterpret_cast<const unsigned long long*>(xb + (size_t)tt * p.D) : 0ull;
+  }
+  float* yb = p.y + (size_t)b * p.T * p.D + c;
+#pragma unroll
+  for (int o = 0; o < TT; ++o) {
+    unsigned long long acc = 0ull;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = dw_ffma2(in[o + j], w[j], acc);
+    if (t0 + o < p.T) *reinterpret_cast<unsigned long long*>(yb + (size_t)(t0 + o) * p.D) = acc;
+  }
+}
+
 }  // namespace
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, float eps,
@@ -287,7 +321,11 @@ int launch_dwconv(const DwConvParams& p, cudaStream_t stream) {
   const size_t total = (size_t)p.B * p.T * p.D;
   if (total == 0) return 0;
   const int threads = ceil_div(p.D, 32) * 32;
-  if (p.K == 32 && threads <= 512) {
+  if (p.K == 32 && p.D % 2 == 0 && p.D <= 512 && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.w)) & 7) == 0) {
+    constexpr int TT = 8;
+    const int th2 = ceil_div(p.D / 2, 32) * 32;
+    B200_CUDA_OK(launch_k(dwconv_reg2_kernel<32, TT>, dim3(ceil_div(p.T, TT), p.B), dim3(th2), 0, stream, p));
+  } else if (p.K == 32 && threads <= 512) {
     constexpr int TT = 8;
     B200_CUDA_OK(launch_k(dwconv_reg_kernel<32, TT>, dim3(ceil_div(p.T, TT), p.B), dim3(threads), 0, stream, p));
   } else if (p.K == 5 && threads <= 512) {
