@@ -35,8 +35,8 @@ FRAMES_PER_UTT = L // HOP
 METRIC = "audio frames/sec (16 kHz, 10 s utts)"
 
 
-def synth_batch(seed: int, B: int = BATCH) -> np.ndarray:
-    """wav ~ N(0, 0.1^2) clipped to [-1, 1]; every 4th row is tiled speech so the decoder emits tokens."""
+def synth_batch(seed: int, B: int = BATCH, L: int = L, speech_every: int = 4) -> np.ndarray:
+    """wav ~ N(0, 0.1^2) clipped to [-1, 1]; every `speech_every`-th row is tiled speech so the decoder emits tokens."""
     rng = np.random.default_rng(seed)
     x = np.clip(rng.standard_normal((B, L)).astype(np.float32) * 0.1, -1.0, 1.0)
     wav_path = os.path.join(ROOT, "tests", "golden", "BAC009S0764W0121.wav")
@@ -44,7 +44,7 @@ def synth_batch(seed: int, B: int = BATCH) -> np.ndarray:
         import wave
         w = wave.open(wav_path)
         s = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768
-        x[::4] = np.tile(s, L // len(s) + 1)[:L]
+        x[::speech_every] = np.tile(s, L // len(s) + 1)[:L]
     return x
 
 

@@ -22,7 +22,8 @@
  * no exception crosses the ABI.  `*_dev` pointers are CUDA device pointers owned by the caller, `*_host` pointers
  * are host memory (pinned memory makes the copies asynchronous).  `stream` is a cudaStream_t passed as void*
  * (NULL = default stream); device-pointer entry points only enqueue work and never synchronise.  The library owns
- * the weight copy and a workspace that grows on demand.  A handle is not thread safe; use one per host thread.
+ * the weight copy and a workspace that grows on demand.  Every entry point takes the handle's mutex, so a handle may be shared between host threads like an onnxruntime session
+ * (calls serialise; use one handle per thread / GPU for concurrency).
  * There is no CPU fallback: creating a handle without a usable sm_100 GPU fails.
  */
 #ifndef B200ASR_H_
@@ -100,6 +101,11 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
 /* wav -> greedy token ids in one call, device buffers. */
 B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev /*[B,T']*/,
                       int32_t* out_len_dev /*[B]*/, void* stream);
+/* Same, honouring per-utterance lengths like tf.keras.backend.ctc_decode(ctc_output, input_length) in the reference's batched
+ * evaluation (asr/tester/am_tester.py:34-40): frame_lengths_dev [B] = number of ENCODER frames of each zero-padded utterance that
+ * are decoded (NULL = all T').  The encoder itself has no padding mask, exactly like the reference's. */
+B200ASR_API int b200asr_recognize_lengths(b200asr_handle h, const float* wav_dev, const int32_t* frame_lengths_dev, int B, int L,
+                                          int32_t* ids_dev /*[B,T']*/, int32_t* out_len_dev /*[B]*/, void* stream);
 /* Same with HOST buffers: H2D of the waveform, compute, D2H of ids + lengths, stream-synchronised on return. */
 B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host,
                            int32_t* out_len_host, void* stream);
@@ -153,6 +159,17 @@ B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const
                                          const float* b2, const float* resid, float* C, float* C2, int M, int K1, int N1, int N2,
                                          float alpha, int epilogue, const float* ln1_g, const float* ln1_b, const float* ln2_g,
                                          const float* ln2_b, float eps, void* stream);
+
+/* Test hooks for the kernels that only the end-to-end path exercised: the conv module's depthwise convolution, and the two
+ * subsampling convolutions (mel [B,T,n_mels] -> [B,T2,F2,D] NHWC) through the engine's precision path. */
+B200ASR_API int b200asr_debug_dwconv(b200asr_handle h, const float* x, const float* w, float* y, int B, int T, int D, int K, int pad_left,
+                                     int round_tf32, void* stream);
+B200ASR_API int b200asr_debug_subsample_convs(b200asr_handle h, const float* mel_dev, int B, int T, float* out_dev, void* stream);
+
+/* Test hook: b200asr_encode without CUDA graph, keeping the residual stream after the subsampler (tap 0) and after every encoder
+ * block (taps 1..num_blocks) in taps_dev [n_taps][B*T', D] -- the tensors the reference's ONNX graph exposes as
+ * conv_subsampling/dense/BiasAdd:0 and conformer_block_<i>/layer_normalization_<5i+4>/add:0 (profiles/r02_stage_errors.md). */
+B200ASR_API int b200asr_debug_encode_taps(b200asr_handle h, const float* wav_dev, int B, int L, float* taps_dev, int n_taps, void* stream);
 
 /* number of kernel launches the library has issued on this handle (bench.py "gpu_launches") */
 B200ASR_API int64_t b200asr_launch_count(b200asr_handle h);

@@ -379,8 +379,11 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
       if (32 * half + 4 * c4 < dh)
-        *reinterpret_cast<float4*>(orow + 4 * c4) =
-            make_float4(o[4 * c4] * inv, o[4 * c4 + 1] * inv, o[4 * c4 + 2] * inv, o[4 * c4 + 3] * inv);
+      {
+        float4 w4 = make_float4(o[4 * c4] * inv, o[4 * c4 + 1] * inv, o[4 * c4 + 2] * inv, o[4 * c4 + 3] * inv);
+        if (p.round_tf32) { w4.x = to_tf32_rn(w4.x); w4.y = to_tf32_rn(w4.y); w4.z = to_tf32_rn(w4.z); w4.w = to_tf32_rn(w4.w); }
+        *reinterpret_cast<float4*>(orow + 4 * c4) = w4;
+      }
     }
   }
   stamp();

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwConvParams p) {
       const int tt = t + j - p.pad_left;
       if (tt >= 0 && tt < p.T) acc = fmaf(xb[(size_t)tt * p.D], p.w[j * p.D + c], acc);
     }
-    p.y[i] = acc;
+    p.y[i] = p.round_tf32 ? tf32_rn(acc) : acc;
   }
 }
 
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(512) dwconv_reg_kernel(const DwConvParams p) {
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) acc = fmaf(in[o + j], w[j], acc);
-    if (t0 + o < p.T) yb[(size_t)(t0 + o) * p.D] = acc;
+    if (t0 + o < p.T) yb[(size_t)(t0 + o) * p.D] = p.round_tf32 ? tf32_rn(acc) : acc;
   }
 }
 
@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(256) dwconv_reg2_kernel(const DwConvParams p) 
     unsigned long long acc = 0ull;
 #pragma unroll
     for (int j = 0; j < K; ++j) acc = dw_ffma2(in[o + j], w[j], acc);
+    if (p.round_tf32) acc = (acc + 0x0000100000001000ull) & 0xFFFFE000FFFFE000ull;   // both halves to nearest tf32 (a carry out of the low half needs bits >= 0xFFFFF000, a NaN)
     if (t0 + o < p.T) *reinterpret_cast<unsigned long long*>(yb + (size_t)(t0 + o) * p.D) = acc;
   }
 }

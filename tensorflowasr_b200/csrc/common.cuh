@@ -95,6 +95,11 @@ __host__ __device__ inline SamePad same_pad(int n_in, int k, int stride) {
   return p;
 }
 
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa on the integer ALU.  The tcgen05 kind::tf32 datapath TRUNCATES whatever
+// fp32 bits it is handed (a -2^-11 relative bias per operand); every tensor that is only ever read as a tensor-core operand is
+// therefore stored already rounded by the kernel that produces it (scripts/tf32_error_study.py: logits error 0.109 -> 0.014).
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -37,9 +39,17 @@ struct Workspace {
 };
 
 struct GraphKey {
-  int kind, B, L;
-  const void *p0, *p1, *p2;
-  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+  int kind = 0, B = 0, L = 0;
+  const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(kind, B, L, p0, p1, p2, p3) < std::tie(o.kind, o.B, o.L, o.p0, o.p1, o.p2, o.p3);
+  }
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;     // kernel launches one replay stands for
+  uint64_t last_use = 0;    // LRU stamp
 };
 
 }  // namespace
@@ -61,8 +71,11 @@ struct b200asr_engine {
   const float *ctc_projw, *ctc_projb, *ctc_fcw, *ctc_fcb;
   int F1 = 0, F2 = 0;  // mel bins after conv1 / conv2
   Workspace ws;
-  std::map<GraphKey, cudaGraphExec_t> graphs;
-  std::map<GraphKey, int64_t> graph_launches;
+  std::map<GraphKey, GraphEntry> graphs;   // at most kMaxGraphs entries, least recently used evicted first
+  uint64_t graph_clock = 0;
+  std::recursive_mutex mu;                 // every C-ABI entry point locks it: a handle may be shared between host threads
+  float* stage_wav = nullptr;              // b200asr_recognize_host: device staging of the waveform (grows on demand)
+  size_t stage_wav_floats = 0;
   int64_t launches = 0;
   std::string err;
   bool use_chain = true;   // chained FFN / conv-tail kernel (B200ASR_NO_CHAIN=1 in the environment turns it off)
@@ -81,6 +94,9 @@ struct b200asr_engine {
     bool busy = false;
   } pipe[2];
   cudaStream_t pipe_copy = nullptr, pipe_compute = nullptr;
+  // b200asr_debug_encode_taps: when set, run_encoder copies the residual stream after the subsampler and after every block
+  float* tap_dst = nullptr;
+  int tap_count = 0, tap_max = 0;
 };
 
 namespace {
@@ -234,9 +250,8 @@ int ensure_workspace(b200asr_handle h, const Shapes& s, Buffers* b) {
   size_t need = carve(h, s, b, nullptr);
   if (need > h->ws.bytes) {
     // growing the workspace invalidates captured graphs (they hold the old addresses)
-    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
-    h->graph_launches.clear();
     ENG_CUDA(h, cudaDeviceSynchronize());
     if (h->ws.base) ENG_CUDA(h, cudaFree(h->ws.base));
     h->ws.base = nullptr;
@@ -254,11 +269,13 @@ struct Ctx {
   cudaStream_t s;
 };
 
+// round_out: the output is only ever read as a tensor-core operand again (store it rounded to nearest tf32)
 int gemm(Ctx& c, const float* A, int lda, const float* W, const float* bias, const float* resid, float alpha, float* C,
-         int ldc, int M, int N, int K, int epi) {
+         int ldc, int M, int N, int K, int epi, bool round_out = false) {
   GemmParams p{};
   p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C;
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.alpha = alpha; p.a_mode = 0;
+  p.round_out = round_out ? 1 : 0;
   c.h->launches++;
   if (c.h->cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(p, epi)) return launch_gemm_tc(c.h->tc, p, epi, c.s);
   return launch_gemm_simt(p, epi, c.s);
@@ -327,7 +344,7 @@ int chain_resid_ln(Ctx& c, const float* X, int K1, const float* W1, const float*
     c.h->launches++;
     return launch_gemm_chain(c.h->tc, cp, epi, c.s);
   }
-  if (gemm(c, X, K1, W1, b1, nullptr, 0.f, b.h, N1, M, N1, K1, EPI_BIAS_SWISH)) return 1;
+  if (gemm(c, X, K1, W1, b1, nullptr, 0.f, b.h, N1, M, N1, K1, EPI_BIAS_SWISH, true)) return 1;
   return gemm_resid_ln(c, b.h, N1, W2, b2, alpha, b, M, D, ln1, ln2, eps);
 }
 
@@ -340,12 +357,14 @@ int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int
   if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
   AttnParams ap{};
   ap.qkv = b.h; ap.out = b.att; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = -1; ap.win_back = 0;
+  ap.round_tf32 = 1;   // (this schedule only runs in tf32 precision)
   if (attention(c, ap)) return 1;
   if (gemm_resid_ln(c, b.att, HD, w.mhsa.wo, w.mhsa.bo, 1.0f, b, M, D, w.conv.ln, nullptr, eps)) return 1;
   if (gemm(c, b.xn, D, w.conv.pw1w, w.conv.pw1b, nullptr, 0.f, b.g, D, M, 2 * D, D, EPI_GLU)) return 1;
   DwConvParams dp{};
   dp.x = b.g; dp.w = w.conv.dww; dp.y = b.att; dp.B = B; dp.T = T; dp.D = D; dp.K = w.kernel_size;
   dp.pad_left = same_pad(T, w.kernel_size, 1).before;
+  dp.round_tf32 = 1;
   c.h->launches++;
   if (launch_dwconv(dp, c.s)) return 1;
   if (chain_resid_ln(c, b.att, D, w.conv.pww, w.conv.pwb, 2 * D, w.conv.pw2w, w.conv.pw2b, 1.0f, b, M, D, w.ffn2.ln, nullptr, eps)) return 1;
@@ -391,6 +410,15 @@ int run_block(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, in
   return 0;
 }
 
+// test hook (b200asr_debug_encode_taps): keep a copy of the residual stream [M, D]
+int tap(Ctx& c, const float* x, size_t floats) {
+  b200asr_handle h = c.h;
+  if (!h->tap_dst || h->tap_count >= h->tap_max) return 0;
+  B200_CUDA_OK(cudaMemcpyAsync(h->tap_dst + (size_t)h->tap_count * floats, x, floats * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+  h->tap_count++;
+  return 0;
+}
+
 int run_frontend(Ctx& c, const float* wav, const Shapes& s, const Buffers& b, float* mel_out) {
   b200asr_handle h = c.h;
   FrontendParams fp{};
@@ -401,40 +429,67 @@ int run_frontend(Ctx& c, const float* wav, const Shapes& s, const Buffers& b, fl
   return launch_frontend(fp, c.s);
 }
 
+int run_subsample_convs(Ctx& c, const float* mel, const Shapes& s, const Buffers& b);
+int run_encoder_tail(Ctx& c, const Shapes& s, const Buffers& b);
+
 // wav [B, L] -> b.x [B*T2, D]
 int run_encoder(Ctx& c, const float* wav, const Shapes& s, const Buffers& b) {
   b200asr_handle h = c.h;
   const b200asr_config& cfg = h->cfg;
   const int D = cfg.dmodel;
   if (run_frontend(c, wav, s, b, b.mel)) return 1;
+  if (run_subsample_convs(c, b.mel, s, b)) return 1;
+  return run_encoder_tail(c, s, b);
+}
+
+// mel [B, T, n_mels] -> b.c2 = relu(conv2(relu(conv1(mel))))  [B, T2, F2, D]
+int run_subsample_convs(Ctx& c, const float* mel, const Shapes& s, const Buffers& b) {
+  b200asr_handle h = c.h;
+  const b200asr_config& cfg = h->cfg;
+  const int D = cfg.dmodel;
   Conv1Params c1{};
-  c1.mel = b.mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
+  c1.mel = mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
   c1.F1 = h->F1; c1.D = D; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
+  c1.round_tf32 = (cfg.precision == B200ASR_PRECISION_TF32) ? 1 : 0;
   h->launches++;
   if (launch_conv1(c1, c.s)) return 1;
   GemmParams g{};
   g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = D; g.K = 9 * D; g.lda = 0; g.ldc = D;
   g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = D; g.pad_t = s.pt2; g.pad_f = s.pf2;
+  g.round_out = 1;   // conv2's output is only read by the subsampling linear layer's GEMM (ignored by the fp32 kernel)
   h->launches++;
   if (cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(g, EPI_BIAS_RELU)) {
     if (launch_gemm_tc(h->tc, g, EPI_BIAS_RELU, c.s)) return 1;
   } else {
     if (launch_gemm_simt(g, EPI_BIAS_RELU, c.s)) return 1;
   }
+  return 0;
+}
+
+// b.c2 -> subsampling linear layer -> encoder blocks -> b.x
+int run_encoder_tail(Ctx& c, const Shapes& s, const Buffers& b) {
+  b200asr_handle h = c.h;
+  const b200asr_config& cfg = h->cfg;
+  const int D = cfg.dmodel;
   if (fused_ln_ok(h) && !h->enc_blocks.empty()) {
     GemmParams lp{};
     lp.A = b.c2; lp.W = h->linw; lp.bias = h->linb; lp.C = b.x; lp.C2 = b.xn; lp.M = s.M; lp.N = D; lp.K = h->F2 * D;
     lp.lda = h->F2 * D; lp.ldc = D; lp.ln1_g = h->enc_blocks[0].ffn1.ln.g; lp.ln1_b = h->enc_blocks[0].ffn1.ln.b; lp.ln_eps = cfg.ln_eps;
     if (gemm_p(c, lp, EPI_BIAS_LN)) return 1;
+    if (tap(c, b.x, (size_t)s.M * D)) return 1;
     for (size_t i = 0; i < h->enc_blocks.size(); ++i) {
       const LNW* next = (i + 1 < h->enc_blocks.size()) ? &h->enc_blocks[i + 1].ffn1.ln : nullptr;
       if (run_block_fused(c, h->enc_blocks[i], b, s.B, s.T2, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps, next)) return 1;
+      if (tap(c, b.x, (size_t)s.M * D)) return 1;
     }
     return 0;
   }
   if (gemm(c, b.c2, h->F2 * D, h->linw, h->linb, nullptr, 0.f, b.x, D, s.M, D, h->F2 * D, EPI_BIAS)) return 1;
-  for (const BlockW& w : h->enc_blocks)
+  if (tap(c, b.x, (size_t)s.M * D)) return 1;
+  for (const BlockW& w : h->enc_blocks) {
     if (run_block(c, w, b, s.B, s.T2, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps)) return 1;
+    if (tap(c, b.x, (size_t)s.M * D)) return 1;
+  }
   return 0;
 }
 
@@ -474,12 +529,22 @@ int run_ctc(Ctx& c, const float* enc, int B, int Tp, const Buffers& b, float* lo
   return 0;
 }
 
-void effective_batch(b200asr_handle h, int* B, int* L) {
+// Block streaming (StreamingConformerEncoder.call, conformer_blocks.py:574-594): an utterance longer than one chunk is reshaped
+// into independent chunks -- tf.reshape there raises unless L is a whole number of chunks, and so does this (encoding such an
+// utterance as one block would silently be a different model: global attention, one dB maximum).  L <= chunk is one (short) chunk.
+int effective_batch(b200asr_handle h, int* B, int* L) {
   const int cs = h->cfg.chunk_samples;
-  if (cs > 0 && *L > cs && (*L % cs) == 0) {
+  if (cs > 0 && *L > cs) {
+    if ((*L % cs) != 0) {
+      snprintf(g_errbuf, sizeof(g_errbuf), "streaming engine: %d samples is not a whole number of %d-sample chunks (split the ragged tail "
+               "off and pass it on its own, as test_asr.py:120-128 does)", *L, cs);
+      if (h) h->err = g_errbuf;
+      return 1;
+    }
     *B = *B * (*L / cs);
     *L = cs;
   }
+  return 0;
 }
 
 // Run `body(stream)` either directly or through a cached CUDA graph keyed on shapes + pointers.  Graphs cannot be
@@ -502,16 +567,20 @@ int with_graph(b200asr_handle h, cudaStream_t s, const GraphKey& key, Body body)
   }
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
-    if (h->graphs.size() >= 32) {
-      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
-      h->graphs.clear();
-      h->graph_launches.clear();
+    constexpr size_t kMaxGraphs = 32;
+    if (h->graphs.size() >= kMaxGraphs) {   // evict the least recently used graph only (a serving loop that rotates through a few
+      auto victim = h->graphs.begin();      // buffer sets keeps its hot graphs)
+      for (auto g = h->graphs.begin(); g != h->graphs.end(); ++g)
+        if (g->second.last_use < victim->second.last_use) victim = g;
+      // the graph may still be executing on a stream: destroying an exec graph is deferred by the runtime until it has finished
+      cudaGraphExecDestroy(victim->second.exec);
+      h->graphs.erase(victim);
     }
     cudaGraph_t graph = nullptr;
     const int64_t before = h->launches;
     ENG_CUDA(h, cudaStreamBeginCapture(rs, cudaStreamCaptureModeThreadLocal));
     int rc = body(rs);
-    h->graph_launches[key] = h->launches - before;
+    const int64_t graph_launches = h->launches - before;
     h->launches = before;
     cudaError_t e = cudaStreamEndCapture(rs, &graph);
     if (rc != 0) {
@@ -540,10 +609,14 @@ int with_graph(b200asr_handle h, cudaStream_t s, const GraphKey& key, Body body)
       snprintf(g_errbuf, sizeof(g_errbuf), "cudaGraphInstantiate: %s", cudaGetErrorString(e));
       return fail_cuda(h);
     }
-    it = h->graphs.emplace(key, exec).first;
+    GraphEntry ge;
+    ge.exec = exec;
+    ge.launches = graph_launches;
+    it = h->graphs.emplace(key, ge).first;
   }
-  ENG_CUDA(h, cudaGraphLaunch(it->second, rs));
-  h->launches += h->graph_launches[key];
+  it->second.last_use = ++h->graph_clock;
+  ENG_CUDA(h, cudaGraphLaunch(it->second.exec, rs));
+  h->launches += it->second.launches;
   if (bridged) {
     ENG_CUDA(h, cudaEventRecord(h->ev_out, rs));
     ENG_CUDA(h, cudaStreamWaitEvent(s, h->ev_out, 0));
@@ -700,7 +773,8 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->stage_wav) cudaFree(h->stage_wav);
   if (h->blob_dev) cudaFree(h->blob_dev);
   if (h->twiddle) cudaFree(h->twiddle);
   if (h->mel_lo) cudaFree(h->mel_lo);
@@ -728,15 +802,16 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
 B200ASR_API int b200asr_out_frames(b200asr_handle h, int num_samples) {
   if (!h || num_samples <= 0) return 0;
   int B = 1, L = num_samples;
-  effective_batch(h, &B, &L);
+  if (effective_batch(h, &B, &L)) return 0;
   return shapes_for(h, 1, L).T2 * B;
 }
 
 B200ASR_API int b200asr_reserve(b200asr_handle h, int B, int L) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B <= 0 || L <= 0) return fail(h, "b200asr_reserve: B and L must be positive");
-  effective_batch(h, &B, &L);
+  if (effective_batch(h, &B, &L)) return 1;
   Buffers b;
   Shapes s = shapes_for(h, B, L);
   return ensure_workspace(h, s, &b);
@@ -746,10 +821,11 @@ B200ASR_API int64_t b200asr_launch_count(b200asr_handle h) { return h ? h->launc
 
 B200ASR_API int b200asr_mel(b200asr_handle h, const float* wav_dev, int B, int L, float* mel_dev, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B < 0 || L <= 0 || !wav_dev || !mel_dev) return fail(h, "b200asr_mel: bad arguments");
   if (B == 0) return 0;
-  effective_batch(h, &B, &L);
+  if (effective_batch(h, &B, &L)) return 1;
   Shapes s = shapes_for(h, B, L);
   Buffers b;
   if (ensure_workspace(h, s, &b)) return 1;
@@ -760,10 +836,11 @@ B200ASR_API int b200asr_mel(b200asr_handle h, const float* wav_dev, int B, int L
 
 B200ASR_API int b200asr_encode(b200asr_handle h, const float* wav_dev, int B, int L, float* enc_dev, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B < 0 || L <= 0 || !wav_dev || !enc_dev) return fail(h, "b200asr_encode: bad arguments");
   if (B == 0) return 0;
-  effective_batch(h, &B, &L);
+  if (effective_batch(h, &B, &L)) return 1;
   Shapes s = shapes_for(h, B, L);
   Buffers b;
   if (ensure_workspace(h, s, &b)) return 1;
@@ -778,8 +855,28 @@ B200ASR_API int b200asr_encode(b200asr_handle h, const float* wav_dev, int B, in
   });
 }
 
+// Test hook: the encoder without CUDA graph, keeping a copy of the residual stream after the subsampler (tap 0) and after each
+// block (taps 1 .. num_blocks) in taps_dev [n_taps][B*T', D]  (per-stage parity table against the reference's ONNX taps).
+B200ASR_API int b200asr_debug_encode_taps(b200asr_handle h, const float* wav_dev, int B, int L, float* taps_dev, int n_taps, void* stream) {
+  if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard dev_guard(h->device);
+  if (B <= 0 || L <= 0 || !wav_dev || !taps_dev || n_taps <= 0) return fail(h, "b200asr_debug_encode_taps: bad arguments");
+  if (effective_batch(h, &B, &L)) return 1;
+  Shapes s = shapes_for(h, B, L);
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  Ctx c{h, static_cast<cudaStream_t>(stream)};
+  h->tap_dst = taps_dev; h->tap_count = 0; h->tap_max = n_taps;
+  const int rc = run_encoder(c, wav_dev, s, b);
+  h->tap_dst = nullptr;
+  if (rc) return fail_cuda(h);
+  return 0;
+}
+
 B200ASR_API int b200asr_ctc_logits(b200asr_handle h, const float* enc_dev, int B, int Tp, float* logits_dev, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (h->cfg.vocab <= 0) return fail(h, "b200asr_ctc_logits: engine was created without a CTC decoder");
   if (B < 0 || Tp < 0 || !enc_dev || !logits_dev) return fail(h, "b200asr_ctc_logits: bad arguments");
@@ -802,6 +899,7 @@ B200ASR_API int b200asr_ctc_logits(b200asr_handle h, const float* enc_dev, int B
 B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank,
                        int32_t* ids_dev, int32_t* out_len_dev, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B < 0 || Tp < 0 || V <= 0 || !ids_dev || !out_len_dev || (!logits_dev && B * Tp > 0))
     return fail(h, "b200asr_ctc_greedy: bad arguments");
@@ -819,6 +917,7 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
                      int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev,
                      void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B < 0 || Tp < 0 || V <= 0 || !ids_dev || !out_len_dev || !scores_dev || (!logits_dev && B * Tp > 0))
     return fail(h, "b200asr_ctc_beam: bad arguments");
@@ -843,20 +942,26 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
 
 B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev, int32_t* out_len_dev,
                       void* stream) {
+  return b200asr_recognize_lengths(h, wav_dev, nullptr, B, L, ids_dev, out_len_dev, stream);
+}
+
+B200ASR_API int b200asr_recognize_lengths(b200asr_handle h, const float* wav_dev, const int32_t* frame_lengths_dev, int B, int L,
+                                          int32_t* ids_dev, int32_t* out_len_dev, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (h->cfg.vocab <= 0) return fail(h, "b200asr_recognize: engine was created without a CTC decoder");
   if (B < 0 || L <= 0 || !wav_dev || !ids_dev || !out_len_dev) return fail(h, "b200asr_recognize: bad arguments");
   if (B == 0) return 0;
   const int B0 = B;
-  effective_batch(h, &B, &L);
+  if (effective_batch(h, &B, &L)) return 1;
   Shapes s = shapes_for(h, B, L);
   Buffers b;
   if (ensure_workspace(h, s, &b)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Tp = s.M / B0;  // frames per original utterance (chunks concatenated in time)
   GraphKey key{};
-  key.kind = 3; key.B = B; key.L = L; key.p0 = wav_dev; key.p1 = ids_dev; key.p2 = out_len_dev;
+  key.kind = 3; key.B = B; key.L = L; key.p0 = wav_dev; key.p1 = ids_dev; key.p2 = out_len_dev; key.p3 = frame_lengths_dev;
   return with_graph(h, st, key, [&](cudaStream_t st) -> int {
     Ctx c{h, st};
     ENG_TRY(h, run_encoder(c, wav_dev, s, b));
@@ -870,11 +975,11 @@ B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B,
     h->launches += 2;
     if (fused_argmax) {
       ENG_TRY(h, run_ctc(c, b.x, B0, Tp, b, nullptr));
-      ENG_TRY(h, launch_ctc_greedy_partials(b.amp, tc_argmax_tiles(h->cfg.vocab), nullptr, B0, Tp, h->cfg.vocab - 1, b.am, ids_dev,
+      ENG_TRY(h, launch_ctc_greedy_partials(b.amp, tc_argmax_tiles(h->cfg.vocab), frame_lengths_dev, B0, Tp, h->cfg.vocab - 1, b.am, ids_dev,
                                             out_len_dev, st));
     } else {
       ENG_TRY(h, run_ctc(c, b.x, B0, Tp, b, b.logits));
-      ENG_TRY(h, launch_ctc_greedy(b.logits, nullptr, B0, Tp, h->cfg.vocab, h->cfg.vocab - 1, b.am, ids_dev, out_len_dev, st));
+      ENG_TRY(h, launch_ctc_greedy(b.logits, frame_lengths_dev, B0, Tp, h->cfg.vocab, h->cfg.vocab - 1, b.am, ids_dev, out_len_dev, st));
     }
     return 0;
   });
@@ -883,23 +988,29 @@ B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B,
 B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, int B, int L, int32_t* ids_host, int32_t* out_len_host,
                            void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B < 0 || L <= 0 || !wav_host || !ids_host || !out_len_host) return fail(h, "b200asr_recognize_host: bad arguments");
   if (B == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // staging buffers live at the end of a workspace sized for this shape
   int Be = B, Le = L;
-  effective_batch(h, &Be, &Le);
+  if (effective_batch(h, &Be, &Le)) return 1;
   Shapes s = shapes_for(h, Be, Le);
   Buffers b;
   if (ensure_workspace(h, s, &b)) return 1;
   const int Tp = s.M / B;
-  // reuse b.power as the device-side waveform staging area is not possible (the frontend writes it); b.c2 is free
-  // until conv2 runs, but the waveform must outlive the STFT only -- use b.att (M*D floats) if large enough, else c2.
-  float* wav_dev = b.c2;
+  // the waveform is staged in a buffer of its own that grows on demand (outside the workspace: any shape works)
   const size_t need = (size_t)B * L;
-  const size_t have = (size_t)s.B * s.T2 * h->F2 * h->cfg.dmodel;
-  if (need > have) return fail(h, "b200asr_recognize_host: staging area too small for this waveform");
+  if (need > h->stage_wav_floats) {
+    ENG_CUDA(h, cudaStreamSynchronize(st));
+    if (h->stage_wav) ENG_CUDA(h, cudaFree(h->stage_wav));
+    h->stage_wav = nullptr; h->stage_wav_floats = 0;
+    // cached graphs keyed on the old staging address can never be hit again; they age out of the LRU cache
+    ENG_CUDA(h, cudaMalloc(&h->stage_wav, need * sizeof(float)));
+    h->stage_wav_floats = need;
+  }
+  float* wav_dev = h->stage_wav;
   ENG_CUDA(h, cudaMemcpyAsync(wav_dev, wav_host, sizeof(float) * need, cudaMemcpyHostToDevice, st));
   if (b200asr_recognize(h, wav_dev, B, L, b.ids, b.lens, st)) return 1;
   ENG_CUDA(h, cudaMemcpyAsync(ids_host, b.ids, sizeof(int32_t) * (size_t)B * Tp, cudaMemcpyDeviceToHost, st));
@@ -911,6 +1022,7 @@ B200ASR_API int b200asr_recognize_host(b200asr_handle h, const float* wav_host, 
 B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const float* wav_host, int B, int L, int32_t* ids_host,
                                   int32_t* out_len_host) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (slot < 0 || slot > 1 || B <= 0 || L <= 0 || !wav_host || !ids_host || !out_len_host)
     return fail(h, "b200asr_recognize_host_submit: bad arguments");
@@ -926,7 +1038,7 @@ B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const 
     ENG_CUDA(h, cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
   }
   int Be = B, Le = L;
-  effective_batch(h, &Be, &Le);
+  if (effective_batch(h, &Be, &Le)) return 1;
   const Shapes s = shapes_for(h, Be, Le);
   const int Tp = s.M / B;
   const size_t nw = (size_t)B * L, ni = (size_t)B * Tp;
@@ -964,6 +1076,7 @@ B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const 
 
 B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (slot < 0 || slot > 1) return fail(h, "b200asr_recognize_host_collect: bad slot");
   auto& ps = h->pipe[slot];
@@ -979,9 +1092,10 @@ B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot) {
 B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, int iters, void* stream, float* ms_per_launch,
                        double* flops, double* bytes) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   if (B <= 0 || L <= 0 || iters <= 0 || !ms_per_launch || !flops || !bytes) return fail(h, "b200asr_time_stage: bad arguments");
-  effective_batch(h, &B, &L);
+  if (effective_batch(h, &B, &L)) return 1;
   Shapes s = shapes_for(h, B, L);
   Buffers b;
   if (ensure_workspace(h, s, &b)) return 1;
@@ -1105,6 +1219,7 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
 B200ASR_API int b200asr_debug_gemm(b200asr_handle h, const float* A, const float* W, const float* bias, const float* resid, float* C,
                        int M, int N, int K, int lda, int ldc, float alpha, int epilogue, int use_tensor_cores, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   GemmParams p{};
   p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldc = ldc; p.alpha = alpha;
@@ -1124,6 +1239,7 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
                           float* C2, int M, int N, int K, float alpha, int epilogue, const float* ln1_g, const float* ln1_b,
                           const float* ln2_g, const float* ln2_b, float eps, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   GemmParams p{};
   p.A = A; p.W = W; p.bias = bias; p.resid = resid; p.C = C; p.C2 = C2; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N;
@@ -1134,10 +1250,43 @@ B200ASR_API int b200asr_debug_gemm_ln(b200asr_handle h, const float* A, const fl
   return 0;
 }
 
+// Test hook: the depthwise convolution of the conv module alone (y[b,t,c] = sum_j x[b, t + j - pad_left, c] * w[j, c]).
+B200ASR_API int b200asr_debug_dwconv(b200asr_handle h, const float* x, const float* w, float* y, int B, int T, int D, int K, int pad_left,
+                                     int round_tf32, void* stream) {
+  if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard dev_guard(h->device);
+  if (!x || !w || !y || B <= 0 || T <= 0 || D <= 0 || K <= 0) return fail(h, "b200asr_debug_dwconv: bad arguments");
+  DwConvParams dp{};
+  dp.x = x; dp.w = w; dp.y = y; dp.B = B; dp.T = T; dp.D = D; dp.K = K; dp.pad_left = pad_left; dp.round_tf32 = round_tf32;
+  h->launches++;
+  ENG_TRY(h, launch_dwconv(dp, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Test hook: the two subsampling convolutions alone: mel [B, T, n_mels] -> relu(conv2(relu(conv1(mel)))) [B, T2, F2, D]
+// (NHWC, the tensor the subsampling linear layer reads), through the engine's own precision path.
+B200ASR_API int b200asr_debug_subsample_convs(b200asr_handle h, const float* mel_dev, int B, int T, float* out_dev, void* stream) {
+  if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard dev_guard(h->device);
+  if (!mel_dev || !out_dev || B <= 0 || T <= 0) return fail(h, "b200asr_debug_subsample_convs: bad arguments");
+  // workspace sized through an equivalent (B, L) with ceil(L / hop) == T
+  Shapes s = shapes_for(h, B, T * h->cfg.hop);
+  if (s.T != T) return fail(h, "b200asr_debug_subsample_convs: internal shape inference mismatch");
+  Buffers b;
+  if (ensure_workspace(h, s, &b)) return 1;
+  Ctx c{h, static_cast<cudaStream_t>(stream)};
+  ENG_TRY(h, run_subsample_convs(c, mel_dev, s, b));
+  ENG_CUDA(h, cudaMemcpyAsync(out_dev, b.c2, sizeof(float) * (size_t)s.B * s.T2 * h->F2 * h->cfg.dmodel, cudaMemcpyDeviceToDevice, c.s));
+  return 0;
+}
+
 // Test hook: one multi-head attention call through the tcgen05 kernel (use_tensor_cores = 1) or the fp32 CUDA-core kernel.
 B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, float* out, int B, int T, int H, int dh, int win_front,
                             int win_back, int use_tensor_cores, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   AttnParams ap{};
   ap.qkv = qkv; ap.out = out; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = win_front; ap.win_back = win_back;
@@ -1156,6 +1305,7 @@ B200ASR_API int b200asr_debug_chain(b200asr_handle h, const float* X, const floa
                         const float* resid, float* C, float* C2, int M, int K1, int N1, int N2, float alpha, int epilogue,
                         const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   ChainGemmParams cp{};
   cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;
@@ -1171,6 +1321,7 @@ B200ASR_API int b200asr_debug_chain_pair(b200asr_handle h, const float* X, const
                              const float* resid, float* C, float* C2, int M, int K1, int N1, int N2, float alpha, int epilogue,
                              const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, float eps, void* stream) {
   if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
   ChainGemmParams cp{};
   cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = resid; cp.C = C; cp.C2 = C2; cp.M = M; cp.K1 = K1; cp.N1 = N1;

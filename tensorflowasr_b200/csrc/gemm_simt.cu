@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const Conv1Params p, int gro
         }
       }
       acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      if (p.round_tf32) { acc.x = tf32_rn(acc.x); acc.y = tf32_rn(acc.y); acc.z = tf32_rn(acc.z); acc.w = tf32_rn(acc.w); }
       *reinterpret_cast<float4*>(orow + (size_t)f1 * p.D) = acc;
     }
   }
@@ -242,7 +243,9 @@ __global__ void __launch_bounds__(256) conv1_f32x2_kernel(const Conv1Params p, i
         }
       }
       const float2 lo = *reinterpret_cast<float2*>(&a_lo), hi = *reinterpret_cast<float2*>(&a_hi);
-      *reinterpret_cast<float4*>(orow + (size_t)f1 * p.D) = make_float4(fmaxf(lo.x, 0.f), fmaxf(lo.y, 0.f), fmaxf(hi.x, 0.f), fmaxf(hi.y, 0.f));
+      float4 o4 = make_float4(fmaxf(lo.x, 0.f), fmaxf(lo.y, 0.f), fmaxf(hi.x, 0.f), fmaxf(hi.y, 0.f));
+      if (p.round_tf32) { o4.x = tf32_rn(o4.x); o4.y = tf32_rn(o4.y); o4.z = tf32_rn(o4.z); o4.w = tf32_rn(o4.w); }
+      *reinterpret_cast<float4*>(orow + (size_t)f1 * p.D) = o4;
     }
   }
 }

@@ -347,6 +347,7 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   tp.ln1_g = p.ln1_g; tp.ln1_b = p.ln1_b; tp.ln2_g = p.ln2_g; tp.ln2_b = p.ln2_b; tp.C2 = p.C2; tp.ln_eps = p.ln_eps;
   tp.num_n_tiles = ceil_div(p.N, bn);
   tp.a_mode = p.a_mode;
+  tp.round_out = p.round_out;
   CUtensorMap ma, mb;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   {

@@ -30,6 +30,7 @@ struct Conv1Params {
   const float* bias;  // [D]
   float* out;         // [B, T1, F1, D]
   int B, T, F, T1, F1, D, pad_t, pad_f;
+  int round_tf32 = 0;   // 1: outputs rounded to nearest tf32 (they feed conv2's tensor-core A operand only)
 };
 int launch_conv1(const Conv1Params& p, cudaStream_t stream);
 
@@ -66,6 +67,9 @@ struct GemmParams {
   // implicit-GEMM geometry for the second subsampling conv (3x3, stride 2, TF 'same')
   int a_mode;          // 0 plain, 1 conv2 im2col
   int T1, F1, T2, F2, D, pad_t, pad_f;
+  // tcgen05 path: store C (plain epilogues) / C2 (LayerNorm epilogues) rounded to nearest tf32 -- set when the tensor is only
+  // read as a tensor-core operand again (the datapath would truncate raw fp32 bits)
+  int round_out = 0;
 };
 int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream);
 
@@ -80,6 +84,7 @@ struct AttnParams {
   // optional band mask (ChunkConformer, chunk_conformer_blocks.py:158-176); win_front < 0 => full attention
   int win_front, win_back;
   long long* dbg = nullptr;   // optional clock64 timeline of CTA 0 (B200ASR_ATTN_DBG=1)
+  int round_tf32 = 0;         // 1: outputs rounded to nearest tf32 (they feed the out-projection's tensor-core A operand only)
 };
 int launch_attention(const AttnParams& p, cudaStream_t stream);          // fp32 CUDA cores (block_ops.cu)
 bool attention_tc_supported(const AttnParams& p);
@@ -90,6 +95,7 @@ struct DwConvParams {
   const float* w;   // [K, D]
   float* y;         // [B*T, D]
   int B, T, D, K, pad_left;
+  int round_tf32 = 0;   // 1: outputs rounded to nearest tf32 (they feed the pointwise conv's tensor-core A operand only)
 };
 int launch_dwconv(const DwConvParams& p, cudaStream_t stream);
 

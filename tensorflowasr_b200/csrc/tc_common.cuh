@@ -30,6 +30,7 @@ struct TcParams {
   int num_m_tiles, num_n_tiles, num_k_blocks;
   // conv2 implicit GEMM
   int a_mode, T2, F2, D, bt, kc, pad_t, pad_f, tiles_per_b;
+  int round_out;   // plain epilogues: store C rounded to nearest tf32 (it is only read as a tensor-core operand again)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -235,6 +236,7 @@ __device__ __forceinline__ void epilogue_plain_group(const TcParams& p, uint32_t
       if (EPI == EPI_BIAS_RELU) v[i] = fmaxf(v[i], 0.f);
       else if (EPI == EPI_BIAS_SWISH) v[i] = swish_fast(v[i]);
       else if (EPI == EPI_RESID) v[i] = r[i] + p.alpha * v[i];
+      if (p.round_out) v[i] = __uint_as_float(tf32_rn_bits(v[i]));
     }
     warp_tile_store<W>(wsm, v, p.C + grow0 * p.ldc + gcol, p.ldc, nrows, p.N - gcol, lane);
   }
@@ -550,6 +552,12 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
       v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
     }
   };
+  // C2 (the LayerNorm-ed copy) is only ever read as the A operand of the next module's GEMMs: store it rounded to nearest tf32
+  // (the tensor core would otherwise truncate it)
+  auto round16 = [&](float* v) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(tf32_rn_bits(v[i]));
+  };
   const float invn = 1.0f / (float)BLOCK_N;
 
   // ---- register-resident path (<= 9 units of 16 columns per thread): every TMEM load of the row segment is issued before the
@@ -697,6 +705,7 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
       float v[16];
       get(u, v);
       affine(v, mean1, rstd1, p.ln1_g, p.ln1_b, u);
+      round16(v);
       put_in(out2, u, v);
     }
     store_tile(map_c2, out2, true);                      // C2 = LN(x; ln1)
@@ -731,6 +740,7 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
     float v[16];
     get(u, v);
     affine(v, mean2, rstd2, p.ln2_g, p.ln2_b, u);
+    round16(v);
     put_in(out2, u, v);
   }
   store_tile(map_c2, out2, true);                        // C2 = LN(y; ln2)

@@ -60,6 +60,7 @@ def load_library() -> ctypes.CDLL:
     if hasattr(lib, "b200asr_ctc_beam"):
         lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
     lib.b200asr_recognize.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.b200asr_recognize_lengths.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_host_submit.argtypes = [vp, ci, vp, ci, ci, vp, vp]
     lib.b200asr_recognize_host_collect.argtypes = [vp, ci]
@@ -70,6 +71,9 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_debug_attention.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.b200asr_debug_chain.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, ci, vp, vp, vp, vp, cf, vp]
     lib.b200asr_debug_chain_pair.argtypes = lib.b200asr_debug_chain.argtypes
+    lib.b200asr_debug_dwconv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.b200asr_debug_subsample_convs.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.b200asr_debug_encode_taps.argtypes = [vp, vp, ci, ci, vp, ci, vp]
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib
@@ -93,7 +97,13 @@ class Engine:
         self.lib = load_library()
         self.device = device
         self.enc_geo, self.ctc_geo = enc_geo, ctc_geo
-        blob = W.pack_blob(W.device_tensors(enc_geo, enc_raw, ctc_geo, ctc_raw))
+        if ctc_geo is not None:
+            # the C config carries one block geometry: the CTC decoder's blocks run with the encoder's head split and widths
+            for f in ("dmodel", "num_heads", "head_size", "ff_dim"):
+                if getattr(ctc_geo, f) != getattr(enc_geo, f):
+                    raise ValueError(f"CTC decoder {f}={getattr(ctc_geo, f)} differs from the encoder's {getattr(enc_geo, f)}: "
+                                     "b200asr_config has a single block geometry")
+        blob = W.pack_blob(W.device_tensors(enc_geo, enc_raw, ctc_geo, ctc_raw, round_tf32=(int(precision) == PRECISION_TF32)))
         cfg = Config()
         cfg.abi_version = self.lib.b200asr_abi_version()
         cfg.dmodel, cfg.num_blocks, cfg.num_heads = enc_geo.dmodel, enc_geo.num_blocks, enc_geo.num_heads
@@ -128,9 +138,8 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f"{what}: " + self.lib.b200asr_last_error(self._h).decode(errors="replace"))
 
-    @staticmethod
-    def _stream() -> int:
-        return int(_torch().cuda.current_stream().cuda_stream)
+    def _stream(self) -> int:
+        return int(_torch().cuda.current_stream(self.device).cuda_stream)
 
     def _dev(self):
         return _torch().device("cuda", self.device)
@@ -228,8 +237,9 @@ class Engine:
                                               self._stream()), "b200asr_ctc_beam")
         return ids, lens, scores
 
-    def recognize(self, wav, ids=None, lens=None):
-        """wav [B, L] on the GPU -> greedy ids [B, T'] (-1 padded) + lengths, all on the GPU (no sync)."""
+    def recognize(self, wav, ids=None, lens=None, frame_lengths=None):
+        """wav [B, L] on the GPU -> greedy ids [B, T'] (-1 padded) + lengths, all on the GPU (no sync).  frame_lengths [B]
+        (encoder frames, int32) = the `input_length` the reference hands to ctc_decode (am_tester.py:39); None = all frames."""
         torch = _torch()
         wav = self._as_wav(wav)
         B, L = wav.shape
@@ -238,9 +248,45 @@ class Engine:
             ids = torch.empty((B, Tp), device=self._dev(), dtype=torch.int32)
         if lens is None:
             lens = torch.empty((B,), device=self._dev(), dtype=torch.int32)
-        self._check(self.lib.b200asr_recognize(self._h, wav.data_ptr(), B, L, ids.data_ptr(), lens.data_ptr(), self._stream()),
-                    "b200asr_recognize")
+        fl = None
+        if frame_lengths is not None:
+            frame_lengths = torch.as_tensor(frame_lengths, dtype=torch.int32).to(self._dev()).contiguous()
+            fl = frame_lengths.data_ptr()
+        self._check(self.lib.b200asr_recognize_lengths(self._h, wav.data_ptr(), fl, B, L, ids.data_ptr(), lens.data_ptr(),
+                                                       self._stream()), "b200asr_recognize")
         return ids, lens
+
+    def encode_taps(self, wav):
+        """Test hook: residual stream after the subsampler and after every encoder block -> [1 + num_blocks, B, T', D]."""
+        torch = _torch()
+        wav = self._as_wav(wav)
+        B, L = wav.shape
+        Tp = self.out_frames(L)
+        n = 1 + self.enc_geo.num_blocks
+        taps = torch.empty((n, B, Tp, self.enc_geo.dmodel), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_debug_encode_taps(self._h, wav.data_ptr(), B, L, taps.data_ptr(), n, self._stream()),
+                    "b200asr_debug_encode_taps")
+        return taps
+
+    def debug_dwconv(self, x, w, pad_left, round_tf32=False):
+        """Test hook: depthwise conv x [B, T, D] (cuda), taps w [K, D] -> y [B, T, D]."""
+        torch = _torch()
+        B, T, D = x.shape
+        y = torch.empty_like(x)
+        self._check(self.lib.b200asr_debug_dwconv(self._h, x.data_ptr(), w.data_ptr(), y.data_ptr(), B, T, D, w.shape[0], int(pad_left),
+                                                  int(bool(round_tf32)), self._stream()), "b200asr_debug_dwconv")
+        return y
+
+    def debug_subsample_convs(self, mel):
+        """Test hook: mel [B, T, n_mels] (cuda) -> relu(conv2(relu(conv1(mel)))) [B, T2, F2, D]."""
+        torch = _torch()
+        B, T, F = mel.shape
+        T1 = -(-T // 2); T2 = -(-T1 // 2)
+        F1 = -(-F // 2); F2 = -(-F1 // 2)
+        out = torch.empty((B, T2, F2, self.enc_geo.dmodel), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_debug_subsample_convs(self._h, mel.contiguous().data_ptr(), B, T, out.data_ptr(), self._stream()),
+                    "b200asr_debug_subsample_convs")
+        return out
 
     def debug_gemm(self, A, Wt, bias=None, resid=None, alpha=1.0, epilogue=0, tensor_cores=True):
         """Test hook: epilogue(A[M,K] @ Wt[N,K].T) on the GPU through one of the two GEMM kernels."""

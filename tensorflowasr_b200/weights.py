@@ -571,8 +571,21 @@ def _pack_block(raw: Dict[str, np.ndarray], src: str, dst: str, out: Dict[str, n
     out[f"{dst}ln.b"] = raw[f"{src}ln.b"]
 
 
+_TC_OPERAND_SUFFIXES = (".w1", ".w2", ".wqkv", ".wo", ".pw1.w", ".pw.w", ".pw2.w")
+_TC_OPERAND_NAMES = ("sub.conv2.w", "sub.lin.w", "ctc.proj.w", "ctc.fc.w")
+
+
+def round_to_tf32(a: np.ndarray) -> np.ndarray:
+    """Round fp32 to the nearest tf32 (10-bit mantissa, ties away from zero) -- bit-exactly what the kernels' tf32_rn does.
+    The tcgen05 kind::tf32 datapath truncates raw fp32 operands; operands rounded beforehand are exact for it."""
+    b = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_geo: Optional[ModelGeometry] = None,
-                   ctc_raw: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+                   ctc_raw: Optional[Dict[str, np.ndarray]] = None, round_tf32: bool = False) -> Dict[str, np.ndarray]:
+    """round_tf32: round every tensor-core GEMM weight to the nearest tf32 (tf32 precision mode only; the exact-fp32 mode
+    keeps the reference's fp32 weights bit for bit)."""
     out: Dict[str, np.ndarray] = {}
     D = enc_geo.dmodel
     out["fe.window"] = enc_raw["fe.window"]
@@ -592,7 +605,12 @@ def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_g
             _pack_block(ctc_raw, f"ctc.blk{i}.", f"ctc.blk{i}.", out)
         out["ctc.fc.w"] = ctc_raw["ctc.fc.w"].T                                                 # [V, D]
         out["ctc.fc.b"] = ctc_raw["ctc.fc.b"]
-    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+    out = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+    if round_tf32:
+        for k in out:
+            if k.endswith(_TC_OPERAND_SUFFIXES) or k in _TC_OPERAND_NAMES:
+                out[k] = round_to_tf32(out[k])
+    return out
 
 
 def pack_blob(tensors: Dict[str, np.ndarray]) -> bytes:

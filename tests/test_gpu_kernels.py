@@ -140,3 +140,62 @@ def test_pair_direct_projection_vs_fp64(keng, torch_mod, M):
         assert not torch.isnan(C2).any()
         assert (C.double() - c_ref).abs().max().item() < 3e-2
         assert (C2.double() - c2_ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("B,T,D,K", [(3, 250, 144, 32), (2, 13, 256, 5), (1, 37, 144, 32), (4, 100, 64, 7), (2, 250, 288, 32)])
+def test_depthwise_conv_kernels_vs_fp64(keng, torch_mod, B, T, D, K):
+    """The conv module's depthwise convolution (SeparableConv1D depthwise part, 'same' = TF SAME_UPPER) alone: the packed
+    fp32x2 register kernel (K = 32, even D), the scalar register kernel (K = 5) and the generic kernel, exact fp32 and with the
+    tf32-rounded store the tensor-core schedule uses."""
+    torch = torch_mod
+    torch.manual_seed(B * 1000 + T + D + K)
+    x = torch.randn(B, T, D, device="cuda")
+    w = torch.randn(K, D, device="cuda") / K ** 0.5
+    total = K - 1
+    pad_left = total // 2
+    xp = torch.nn.functional.pad(x.double(), (0, 0, pad_left, total - pad_left))
+    ref = sum(xp[:, j:j + T, :] * w[j].double() for j in range(K))
+    y = keng.debug_dwconv(x, w, pad_left)
+    yr = keng.debug_dwconv(x, w, pad_left, round_tf32=True)
+    torch.cuda.synchronize()
+    assert (y.double() - ref).abs().max().item() < 2e-5
+    assert (yr.double() - ref).abs().max().item() < 2e-5 + ref.abs().max().item() * 2.0 ** -11
+    assert (yr.view(torch.int32) & 0x1FFF).abs().max().item() == 0          # stored values are exact tf32 numbers
+    causal = keng.debug_dwconv(x, w, K - 1)                                  # the ChunkConformer's causal variant (pad_left = K - 1)
+    xc = torch.nn.functional.pad(x.double(), (0, 0, K - 1, 0))
+    refc = sum(xc[:, j:j + T, :] * w[j].double() for j in range(K))
+    assert (causal.double() - refc).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,T", [(2, 1000), (3, 421), (1, 7), (2, 50)])
+def test_subsampling_convs_vs_fp64(torch_mod, B, T):
+    """conv1 (3x3 s2 'same', 1 -> D, ReLU; CUDA cores) + conv2 (3x3 s2 'same', D -> D, ReLU; implicit GEMM on tcgen05 with the
+    4-D strided TMA A operand, a_mode 1) against torch conv2d in fp64, tf32 engine and exact-fp32 engine.  Odd T exercises
+    every TF SAME_UPPER padding branch."""
+    torch = torch_mod
+    from tensorflowasr_b200 import engine as E, weights as W
+    ge, re_, gc, rc = W.random_model(5, num_blocks=1)
+    D = ge.dmodel
+    torch.manual_seed(B * 31 + T)
+    mel = (torch.randn(B, T, 80, device="cuda") * 20 - 40)
+    w1 = torch.from_numpy(re_["sub.conv1.w"]).cuda().double()            # [3, 3, 1, D] HWIO
+    b1 = torch.from_numpy(re_["sub.conv1.b"]).cuda().double()
+    w2 = torch.from_numpy(re_["sub.conv2.w"]).cuda().double()            # [3, 3, D, D]
+    b2 = torch.from_numpy(re_["sub.conv2.b"]).cuda().double()
+
+    def same_conv(x, w, b):                                              # x [B, C, H, W]; TF 'same' stride 2: extra pad at the end
+        H, Wd = x.shape[2], x.shape[3]
+        ph = max((-(-H // 2) - 1) * 2 + 3 - H, 0)
+        pw = max((-(-Wd // 2) - 1) * 2 + 3 - Wd, 0)
+        x = torch.nn.functional.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+        return torch.relu(torch.nn.functional.conv2d(x, w.permute(3, 2, 0, 1), b, stride=2))
+
+    ref = same_conv(same_conv(mel.double()[:, None], w1, b1), w2, b2).permute(0, 2, 3, 1)     # [B, T2, F2, D]
+    for prec, tol in ((1, 1e-3), (0, 3e-2 * max(1.0, ref.abs().max().item() / 100))):
+        e = E.Engine(ge, re_, gc, rc, precision=prec, use_cuda_graph=False)
+        got = e.debug_subsample_convs(mel)
+        torch.cuda.synchronize()
+        assert tuple(got.shape) == tuple(ref.shape)
+        err = (got.double() - ref).abs().max().item()
+        assert err < tol, (prec, err, ref.abs().max().item())
+        e.close()

@@ -4,7 +4,8 @@ from the reference itself.
 
 Tolerances (stated per north_star "within a stated fp32 tolerance"):
   * fp32 mode (CUDA-core GEMMs): |enc - oracle| <= 2e-4, |logits - oracle| <= 2e-3 (values up to ~30)
-  * tf32 mode (tcgen05 tensor cores, fp32 accumulate): |enc - oracle| <= 3e-2, |logits - oracle| <= 0.25
+  * tf32 mode (tcgen05 tensor cores, fp32 accumulate, every operand rounded to nearest tf32 by its producer):
+    |enc - oracle| <= 8e-3, |logits - oracle| <= 3e-2 (scripts/tf32_error_study.py predicts 1.8e-3 / 1.5e-2)
   * mel (always fp32): 5e-3 dB on a [-80, 0] scale
   * token ids (greedy, beam): bit-exact
 """
@@ -17,7 +18,7 @@ from conftest import GOLDEN_IDS
 
 pytestmark = pytest.mark.gpu
 
-TOL = {1: dict(enc=2e-4, logits=2e-3), 0: dict(enc=3e-2, logits=0.25)}
+TOL = {1: dict(enc=2e-4, logits=2e-3), 0: dict(enc=8e-3, logits=3e-2)}
 
 
 @pytest.fixture(scope="module")
@@ -106,8 +107,7 @@ def test_noise_batch_vs_oracle_and_golden(eng, offline_weights, golden, noise_2x
     np.testing.assert_allclose(enc, golden["noise_enc"], atol=tol["enc"] + 3e-4)
     ids, lens = eng.recognize(noise_2x2s)
     logits = eng.ctc_logits(eng.encode(noise_2x2s)).cpu().numpy()
-    if eng.precision == 1:
-        assert (logits.argmax(-1) == golden["noise_argmax"]).all()
+    assert (logits.argmax(-1) == golden["noise_argmax"]).all()       # both precision modes: the reference's per-frame argmax
 
 
 @pytest.mark.parametrize("L", [640, 4000, 8000, 12345, 31999])
