@@ -330,8 +330,9 @@ int gemm_resid_ln(Ctx& c, const float* A, int K, const float* W, const float* bi
 // x = x + alpha * (swish(X.W1^T + b1).W2^T + b2) with the LayerNorm epilogue(s), as ONE chained kernel when supported,
 // else as two GEMMs through the wide scratch buffer b.h.
 int chain_resid_ln(Ctx& c, const float* X, int K1, const float* W1, const float* b1, int N1, const float* W2, const float* b2, float alpha,
-                   const Buffers& b, int M, int D, const LNW& ln1, const LNW* ln2, float eps) {
+                   const Buffers& b, int M, int D, const LNW& ln1, const LNW* ln2, float eps, bool round_c = false) {
   ChainGemmParams cp{};
+  cp.round_c = round_c ? 1 : 0;
   cp.X = X; cp.W1 = W1; cp.bias1 = b1; cp.W2 = W2; cp.bias2 = b2; cp.resid = b.x; cp.C = b.x; cp.C2 = b.xn; cp.M = M; cp.K1 = K1;
   cp.N1 = N1; cp.N2 = D; cp.ldx = K1; cp.alpha = alpha; cp.ln1_g = ln1.g; cp.ln1_b = ln1.b; cp.ln_eps = eps;
   if (ln2) { cp.ln2_g = ln2->g; cp.ln2_b = ln2->b; }
@@ -350,8 +351,9 @@ int chain_resid_ln(Ctx& c, const float* X, int K1, const float* W1, const float*
 
 // One ConformerBlock with every LayerNorm folded into the epilogue of the GEMM that produces its input (11 launches).
 // Pre-condition: b.xn == LN(b.x; w.ffn1.ln).  Post-condition: b.x = block output, b.xn = LN(b.x; *next_ln) if next_ln.
+// round_out: the block output only feeds another GEMM (the CTC head): store it rounded to nearest tf32.
 int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int D, int F, int H, int dh, float eps,
-                    const LNW* next_ln) {
+                    const LNW* next_ln, bool round_out = false) {
   const int M = B * T, HD = H * dh;
   if (chain_resid_ln(c, b.xn, D, w.ffn1.w1, w.ffn1.b1, F, w.ffn1.w2, w.ffn1.b2, 0.5f, b, M, D, w.mhsa.ln, nullptr, eps)) return 1;
   if (gemm(c, b.xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, b.h, 3 * HD, M, 3 * HD, D, EPI_NONE)) return 1;
@@ -369,7 +371,8 @@ int run_block_fused(Ctx& c, const BlockW& w, const Buffers& b, int B, int T, int
   if (launch_dwconv(dp, c.s)) return 1;
   if (chain_resid_ln(c, b.att, D, w.conv.pww, w.conv.pwb, 2 * D, w.conv.pw2w, w.conv.pw2b, 1.0f, b, M, D, w.ffn2.ln, nullptr, eps)) return 1;
   LNW none{nullptr, nullptr};
-  if (chain_resid_ln(c, b.xn, D, w.ffn2.w1, w.ffn2.b1, F, w.ffn2.w2, w.ffn2.b2, 0.5f, b, M, D, w.ln, next_ln ? next_ln : &none, eps)) return 1;
+  if (chain_resid_ln(c, b.xn, D, w.ffn2.w1, w.ffn2.b1, F, w.ffn2.w2, w.ffn2.b2, 0.5f, b, M, D, w.ln, next_ln ? next_ln : &none, eps,
+                     round_out && !next_ln)) return 1;
   return 0;
 }
 
@@ -508,7 +511,7 @@ int run_ctc(Ctx& c, const float* enc, int B, int Tp, const Buffers& b, float* lo
     if (gemm_p(c, pp, EPI_BIAS_LN)) return 1;
     for (size_t i = 0; i < h->ctc_blocks.size(); ++i) {
       const LNW* next = (i + 1 < h->ctc_blocks.size()) ? &h->ctc_blocks[i + 1].ffn1.ln : nullptr;
-      if (run_block_fused(c, h->ctc_blocks[i], bb, B, Tp, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps, next)) return 1;
+      if (run_block_fused(c, h->ctc_blocks[i], bb, B, Tp, D, cfg.ff_dim, cfg.num_heads, cfg.head_size, cfg.ln_eps, next, true)) return 1;
     }
     if (logits == nullptr) {
       // greedy path: the CTC head keeps only per-tile (max, argmax) pairs (EPI_BIAS_ARGMAX); no logits are written

@@ -369,6 +369,7 @@ int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cu
   cp.ep.bias = p.bias2; cp.ep.resid = p.resid; cp.ep.C = p.C; cp.ep.C2 = p.C2; cp.ep.M = p.M; cp.ep.N = p.N2; cp.ep.K = p.N1;
   cp.ep.ldc = p.N2; cp.ep.alpha = p.alpha; cp.ep.ln1_g = p.ln1_g; cp.ep.ln1_b = p.ln1_b; cp.ep.ln2_g = p.ln2_g; cp.ep.ln2_b = p.ln2_b;
   cp.ep.ln_eps = p.ln_eps;
+  cp.ep.round_out = (p.round_c && p.ln2_g == nullptr) ? 1 : 0;
   cp.bias1 = p.bias1;
   cp.n_chunks = p.N1 / CH;
   cp.kb1 = ceil_div(p.K1, 32);

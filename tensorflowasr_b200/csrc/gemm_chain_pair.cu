@@ -440,6 +440,7 @@ int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogu
   pp.ep.bias = p.bias2; pp.ep.resid = p.resid; pp.ep.C = p.C; pp.ep.C2 = p.C2; pp.ep.M = p.M; pp.ep.N = p.N2; pp.ep.K = p.N1;
   pp.ep.ldc = p.N2; pp.ep.alpha = p.alpha; pp.ep.ln1_g = p.ln1_g; pp.ep.ln1_b = p.ln1_b; pp.ep.ln2_g = p.ln2_g; pp.ep.ln2_b = p.ln2_b;
   pp.ep.ln_eps = p.ln_eps;
+  pp.ep.round_out = (p.round_c && p.ln2_g == nullptr) ? 1 : 0;
   pp.bias1 = p.bias1;
   const bool direct = (p.N1 == 0);
   pp.nl = direct ? 0 : p.N1 / CH / 2;

@@ -23,6 +23,7 @@ struct ChainGemmParams {
   float alpha;
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   float ln_eps;
+  int round_c = 0;   // EPI_RESID_LN2 without a second LayerNorm: store C rounded to nearest tf32 (it only feeds another GEMM)
 };
 bool tc_chain_supported(const ChainGemmParams& p, int epilogue);
 int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);

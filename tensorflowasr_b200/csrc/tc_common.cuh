@@ -724,6 +724,7 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
       t1 += d;
       t2 = fmaf(d, d, t2);
     }
+    if (p.round_out) round16(v);   // (set only when no second LayerNorm follows: C is then read as a tensor-core operand only)
     put(u, v);
   }
   if (p.ln2_g == nullptr) {

@@ -73,3 +73,52 @@ def streaming_weights():
 def noise_2x2s():
     rng = np.random.default_rng(7)
     return np.clip(rng.standard_normal((2, 32000)).astype(np.float32) * 0.1, -1, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------- tolerances
+# Stated tolerances of the two precision modes against the reference (fp32 ONNX graphs) / the fp64 oracle.
+#   fp32 mode (CUDA-core GEMMs): encoder states 2e-4, logits 2e-3 -- and ids / per-frame argmax identical, no exceptions.
+#   tf32 mode (tcgen05, every operand rounded to nearest tf32 by its producer): encoder states 8e-3 (measured 3.7e-3 on values
+#     up to 8, i.e. 2^-11 relative: the rounding floor of one tf32 operand), logits rms 1e-2 and max 0.15.  The max is an outlier
+#     bound: the reference's CTC decoder amplifies a 1e-3 perturbation of the encoder output up to 100x on single elements (conv
+#     module x12, final LayerNorm gain 8; scripts/tf32_error_study.py, profiles/r02_stage_errors.md), so no single-pass tf32
+#     arithmetic can hold the 2e-2 that the rms suggests.  Greedy ids are identical to the reference wherever the reference's own
+#     top-2 logit margin exceeds 2 x the max tolerance; a frame inside that margin may legitimately flip (assert_ids_match).
+TOL_ENC = {1: 2e-4, 0: 8e-3}
+TOL_LOGITS_MAX = {1: 2e-3, 0: 0.15}
+TOL_LOGITS_RMS = {1: 2e-4, 0: 1e-2}
+
+
+def check_logits(got, ref, precision, what=""):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    d = got - ref
+    mx, rms = float(np.abs(d).max()), float(np.sqrt(np.mean(d * d)))
+    print(f"{what} precision {precision}: logits max |err| {mx:.3e}, rms {rms:.3e}")
+    assert mx <= TOL_LOGITS_MAX[precision], (what, mx)
+    assert rms <= TOL_LOGITS_RMS[precision], (what, rms)
+    return mx, rms
+
+
+def assert_ids_match(got_ids, got_logits_row, ref_logits_row, precision, blank=None, what=""):
+    """got_ids == greedy(ref_logits_row): exactly in fp32 mode.  In tf32 mode a frame whose top-2 margin in the reference is
+    below 2 x TOL_LOGITS_MAX is undecidable at the stated tolerance: the per-frame argmax of the device logits may differ from the
+    reference's on such frames ONLY, and got_ids must be the CTC collapse of the device's own argmax sequence.  Returns the number
+    of frames that flipped (0 in the common case)."""
+    from oracle import ctc_ref
+    ref_logits_row, got_logits_row = np.asarray(ref_logits_row), np.asarray(got_logits_row)
+    blank = ref_logits_row.shape[-1] - 1 if blank is None else blank
+    want = ctc_ref.greedy_decode(ref_logits_row, blank)
+    ga, ra = got_logits_row.argmax(-1), ref_logits_row.argmax(-1)
+    flipped = np.nonzero(ga != ra)[0]
+    if len(flipped) == 0:
+        assert list(got_ids) == want, (what, list(got_ids), want)
+        return 0
+    assert precision == 0, (what, "exact mode: a per-frame argmax differs from the reference at frames", flipped.tolist())
+    top2 = np.sort(ref_logits_row[flipped], axis=-1)[:, -2:]
+    margin = top2[:, 1] - top2[:, 0]
+    assert (margin < 2 * TOL_LOGITS_MAX[0]).all(), (what, "argmax flipped on a frame the reference decides by more than the tolerance",
+                                                    flipped.tolist(), margin.tolist())
+    assert list(got_ids) == ctc_ref.greedy_decode(got_logits_row, blank), (what, "ids are not the collapse of the device's own argmax")
+    print(f"{what}: {len(flipped)} low-margin frame(s) flipped (reference margins {np.round(margin, 4).tolist()})")
+    return len(flipped)
