@@ -395,7 +395,10 @@ def main():
                             "(profiles/r01_ubench_mma_tf32_pacing.txt): the kernel is bound by its MMA instruction count, not by bytes"}
             others = {}
             for st in ("conv2", "stft", "conv1", "qkv", "attention", "dwconv", "sub_linear", "ctc_fc"):
-                others[st] = stage_line(st)[3]
+                try:
+                    others[st] = stage_line(st)[3]
+                except RuntimeError as ex:            # e.g. conv1 has no kernel of its own when it is fused into conv2's
+                    others[st] = {"skipped": str(ex)[:160]}
             roof["other_stages"] = others
 
     t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)

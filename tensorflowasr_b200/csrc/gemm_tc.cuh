@@ -33,4 +33,19 @@ bool tc_chain_pair_supported(const ChainGemmParams& p, int epilogue);
 bool tc_pair_direct_supported(const ChainGemmParams& p, int epilogue);
 int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogue, cudaStream_t stream);
 
+// ConvSubsampling's two convolutions as one kernel (conv_sub_tc.cu): conv1 computed on the fly into conv2's implicit-GEMM A tile.
+struct ConvSubParams {
+  const float* mel;   // [B, T, F]
+  const float* w1;    // [9, D] tap-major (conv1: 1 -> D)
+  const float* b1;    // [D]
+  const float* w2;    // [D, 9 D] K-major: [cout][(kh, kw, cin)]
+  const float* b2;    // [D]
+  float* out;         // [B, T2, F2, D]
+  int B, T, F, T1, F1, T2, F2, D;
+  int pt1, pf1, pt2, pf2;   // 'same' padding before (time / frequency) of conv1 and conv2
+  int round_out;            // store the output rounded to nearest tf32 (it feeds the subsampling linear GEMM only)
+};
+bool conv_subsample_tc_supported(const ConvSubParams& p);
+int launch_conv_subsample_tc(TcContext& ctx, const ConvSubParams& p, cudaStream_t stream);
+
 }  // namespace b200asr
