@@ -119,6 +119,51 @@ B200ASR_API int b200asr_recognize_host_submit(b200asr_handle h, int slot, const 
                                               int32_t* out_len_host);
 B200ASR_API int b200asr_recognize_host_collect(b200asr_handle h, int slot);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * ChunkConformer: causal chunk streaming with state caches (asr/models/chunk_conformer_blocks.py, driven by test_chunk_asr.py:47-139).
+ * A chunk engine is created from its own weight blob (tensorflowasr_b200.chunk_model.pack_chunk_blob) and uses the tcgen05 path
+ * only.  A stream state holds the caches of B streams that advance in lockstep (one state per group of concurrent streams; a
+ * state belongs to one handle, i.e. one GPU, for its lifetime -- SURVEY 8e).
+ *
+ *   b200asr_stream_step           <-> ChunkConformer.picker_stream_predict (:807-824): front end (wav cache 2560 samples, mel cache
+ *                                     4 frames) -> 15 causal encoder blocks with K|V / conv caches -> picker block -> phone logits
+ *   b200asr_stream_feature_pick   <-> ChunkConformer.feature_pick (:913-999): keep the frames whose phone argmax is not blank
+ *   b200asr_stream_decoder_step   <-> ChunkConformer.decoder_stream_predict (:826-837): helper blocks -> decoder block with
+ *                                     `dec_back` frames of look-ahead (the frames still inside it are carried to the next call)
+ */
+typedef struct b200asr_stream_state* b200asr_stream;
+
+typedef struct {
+  int32_t abi_version;                                   /* B200ASR_ABI_VERSION */
+  int32_t dmodel, num_heads, head_size, kernel_size, ff_dim;   /* chunk_conformerS.yml model_config */
+  int32_t enc_blocks, picker_blocks, helper_blocks, dec_blocks;
+  int32_t win_front, picker_back, dec_back;              /* attention band: frames back / look-ahead of picker and decoder */
+  int32_t phone_classes, txt_classes;                    /* real class counts incl. blank (= last); the blob pads both heads to a multiple of 4 */
+  int32_t n_mels, n_dft, hop, chunk_num, reduction;      /* chunk_num mel frames per step (16 = 160 ms, 32 = 320 ms), reduction 4 */
+  float ln_eps;
+  int32_t use_cuda_graph;
+  int32_t reserved[8];
+} b200asr_chunk_config;
+
+B200ASR_API int b200asr_chunk_create(const void* weight_blob, size_t blob_bytes, const b200asr_chunk_config* cfg, int device, b200asr_handle* out);
+B200ASR_API int b200asr_stream_state_create(b200asr_handle h, int B, b200asr_stream* out);
+B200ASR_API int b200asr_stream_state_reset(b200asr_handle h, b200asr_stream st);     /* init_picker_caches / init_decoder_caches (:777-792) */
+B200ASR_API int b200asr_stream_state_destroy(b200asr_handle h, b200asr_stream st);
+/* One picker step: wav_chunk_dev [B, chunk_num*hop] -> phone_logits_dev [B, T, phone_classes], hidden_dev [B, T, dmodel], T = chunk_num / reduction. */
+B200ASR_API int b200asr_stream_step(b200asr_handle h, b200asr_stream st, const float* wav_chunk_dev, float* phone_logits_dev, float* hidden_dev,
+                                    void* stream);
+/* feats_dev [B, T, dmodel] (kept rows first, zero rows behind), picked_logits_dev [B, T, V] (nullable), counts_dev [B]; when
+ * n_max_host != NULL the call synchronises `stream` and stores the largest count there (the caller needs it to shape the decoder input). */
+B200ASR_API int b200asr_stream_feature_pick(b200asr_handle h, const float* hidden_dev, const float* phone_logits_dev, int B, int T, int V, int blank,
+                                            float* feats_dev, float* picked_logits_dev, int32_t* counts_dev, int32_t* n_max_host, void* stream);
+/* One decoder step on n picked frames per stream (feats_dev [B, n, dmodel] contiguous, n >= 1).  Writes the text logits of the carried +
+ * new frames, txt_logits_dev [B, n_rows, txt_classes] with n_rows = carried + n <= dec_back + n; the first *n_valid_host rows of each
+ * stream are final ("valid"), the remaining n_rows - n_valid are still inside the look-ahead ("unvalid") and are re-fed by the next call. */
+B200ASR_API int b200asr_stream_decoder_step(b200asr_handle h, b200asr_stream st, const float* feats_dev, int n, float* txt_logits_dev,
+                                            int32_t* n_rows_host, int32_t* n_valid_host, void* stream);
+/* rows the next decoder step will produce for n new frames (= carried frames + n) */
+B200ASR_API int b200asr_stream_decoder_rows(b200asr_handle h, b200asr_stream st, int n);
+
 /* Roofline instrumentation (bench.py): time one stage of the schedule alone, `iters` launches bracketed by CUDA events on
  * `stream`; also returns that launch's algorithmic FLOPs and HBM bytes.  Run b200asr_recognize with the same (B, L) first. */
 enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 = 2, B200ASR_STAGE_STFT = 3,

@@ -63,6 +63,7 @@ size_t carve(b200asr_handle h, const Shapes& s, Buffers* b, char* base) {
 }
 
 int ensure_workspace(b200asr_handle h, const Shapes& s, Buffers* b) {
+  if (h->chunk) return fail(h, "this handle is a ChunkConformer engine: use the b200asr_stream_* entry points");
   size_t need = carve(h, s, b, nullptr);
   if (need > h->ws.bytes) {
     // growing the workspace invalidates captured graphs (they hold the old addresses)
@@ -292,92 +293,68 @@ int effective_batch(b200asr_handle h, int* B, int* L) {
 
 }  // namespace
 
-// ================================================================================================== C ABI
-extern "C" {
+// ================================================================================================== shared with chunk_engine.cu
+namespace b200asr {
 
-B200ASR_API int b200asr_abi_version(void) { return B200ASR_ABI_VERSION; }
-
-B200ASR_API const char* b200asr_last_error(b200asr_handle h) { return h ? h->err.c_str() : g_errbuf; }
-
-B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const b200asr_config* cfg, int device, b200asr_handle* out) {
-  if (!weight_blob || !cfg || !out) return fail(nullptr, "b200asr_create: null argument");
-  if (cfg->abi_version != B200ASR_ABI_VERSION) return fail(nullptr, "b200asr_create: ABI version mismatch");
+// device / blob checks, new handle with the weight blob resident on `device` and the tensor table filled.  h->cfg is left to the caller.
+int engine_alloc(const void* weight_blob, size_t blob_bytes, int device, const char* who, b200asr_engine** out) {
   *out = nullptr;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(nullptr, "b200asr_create: no CUDA device (this library has no CPU fallback)");
-  if (device < 0 || device >= ndev) return fail(nullptr, "b200asr_create: bad device index");
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "%s: no CUDA device (this library has no CPU fallback)", who);
+    return 1;
+  }
+  if (device < 0 || device >= ndev) { snprintf(g_errbuf, sizeof(g_errbuf), "%s: bad device index", who); return 1; }
   cudaDeviceProp prop;
   ENG_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
-    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: device %d is sm_%d%d; this build targets sm_100a (B200) only", device,
-             prop.major, prop.minor);
+    snprintf(g_errbuf, sizeof(g_errbuf), "%s: device %d is sm_%d%d; this build targets sm_100a (B200) only", who, device, prop.major, prop.minor);
     return 1;
   }
   ENG_CUDA(nullptr, cudaSetDevice(device));
-  if (blob_bytes < 16 || memcmp(weight_blob, "B2ASRW01", 8) != 0) return fail(nullptr, "b200asr_create: bad weight blob magic");
+  if (blob_bytes < 16 || memcmp(weight_blob, "B2ASRW01", 8) != 0) { snprintf(g_errbuf, sizeof(g_errbuf), "%s: bad weight blob magic", who); return 1; }
   const char* hb = static_cast<const char*>(weight_blob);
   uint32_t n_entries;
   memcpy(&n_entries, hb + 8, 4);
   const size_t table_end = 16 + (size_t)n_entries * sizeof(BlobEntry);
-  if (table_end > blob_bytes) return fail(nullptr, "b200asr_create: truncated weight blob");
-
+  if (table_end > blob_bytes) { snprintf(g_errbuf, sizeof(g_errbuf), "%s: truncated weight blob", who); return 1; }
   b200asr_engine* h = new b200asr_engine();
-  h->cfg = *cfg;
   h->device = device;
-  auto bail = [&](int) {
-    std::string e = g_errbuf;
-    b200asr_destroy(h);
-    snprintf(g_errbuf, sizeof(g_errbuf), "%s", e.c_str());
-    return 1;
-  };
   if (cudaMalloc(&h->blob_dev, blob_bytes) != cudaSuccess ||
       cudaMemcpy(h->blob_dev, weight_blob, blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: cannot place %zu weight bytes on device", blob_bytes);
-    return bail(1);
+    snprintf(g_errbuf, sizeof(g_errbuf), "%s: cannot place %zu weight bytes on device", who, blob_bytes);
+    b200asr_destroy(h);
+    return 1;
   }
   for (uint32_t i = 0; i < n_entries; ++i) {
     BlobEntry e;
     memcpy(&e, hb + 16 + (size_t)i * sizeof(BlobEntry), sizeof(BlobEntry));
     e.name[47] = 0;
     if (e.offset % 128 != 0 || e.offset + e.numel * 4 > blob_bytes) {
-      snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: entry '%s' out of bounds / misaligned", e.name);
-      return bail(1);
+      snprintf(g_errbuf, sizeof(g_errbuf), "%s: entry '%s' out of bounds / misaligned", who, e.name);
+      std::string keep = g_errbuf;
+      b200asr_destroy(h);
+      snprintf(g_errbuf, sizeof(g_errbuf), "%s", keep.c_str());
+      return 1;
     }
     h->tensors[e.name] = {reinterpret_cast<const float*>(h->blob_dev + e.offset), e.numel};
   }
+  *out = h;
+  return 0;
+}
+
+// frontend tables (window, FFT twiddles, sparse mel filters), the tensor-map encoder and the environment switches.
+// Needs h->cfg.{n_dft, n_mels} and the host copy of the blob (the mel filters' sparsity pattern is analysed on the host).
+int engine_init_frontend(b200asr_engine* h, const void* weight_blob) {
   const b200asr_config& c = h->cfg;
-  if (c.n_dft != 1024) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: n_dft must be 1024 (reference hard-codes it)"); return bail(1); }
-  if (c.dmodel % 16 != 0 || c.dmodel > 512) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: dmodel must be a multiple of 16, <= 512"); return bail(1); }
-  const int D = c.dmodel, nb = c.n_dft / 2 + 1;
-  h->F1 = same_pad(c.n_mels, 3, 2).out;
-  h->F2 = same_pad(h->F1, 3, 2).out;
+  const char* hb = static_cast<const char*>(weight_blob);
+  uint32_t n_entries;
+  memcpy(&n_entries, hb + 8, 4);
+  const int nb = c.n_dft / 2 + 1;
   bool ok = true;
   h->window = lookup(h, "fe.window", c.n_dft, &ok);
   h->melw = ok ? lookup(h, "fe.mel", (uint64_t)nb * c.n_mels, &ok) : nullptr;
-  h->c1w = ok ? lookup(h, "sub.conv1.w", 9ull * D, &ok) : nullptr;
-  h->c1b = ok ? lookup(h, "sub.conv1.b", D, &ok) : nullptr;
-  h->c2w = ok ? lookup(h, "sub.conv2.w", 9ull * D * D, &ok) : nullptr;
-  h->c2b = ok ? lookup(h, "sub.conv2.b", D, &ok) : nullptr;
-  h->linw = ok ? lookup(h, "sub.lin.w", (uint64_t)h->F2 * D * D, &ok) : nullptr;
-  h->linb = ok ? lookup(h, "sub.lin.b", D, &ok) : nullptr;
-  if (!ok) return bail(1);
-  h->enc_blocks.resize(c.num_blocks);
-  for (int i = 0; i < c.num_blocks; ++i)
-    if (!load_block(h, "enc." + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.kernel_size, &h->enc_blocks[i]))
-      return bail(1);
-  if (c.vocab > 0) {
-    h->ctc_projw = lookup(h, "ctc.proj.w", (uint64_t)D * D, &ok);
-    h->ctc_projb = ok ? lookup(h, "ctc.proj.b", D, &ok) : nullptr;
-    h->ctc_fcw = ok ? lookup(h, "ctc.fc.w", (uint64_t)c.vocab * D, &ok) : nullptr;
-    h->ctc_fcb = ok ? lookup(h, "ctc.fc.b", c.vocab, &ok) : nullptr;
-    if (!ok) return bail(1);
-    h->ctc_blocks.resize(c.ctc_blocks);
-    for (int i = 0; i < c.ctc_blocks; ++i)
-      if (!load_block(h, "ctc.blk" + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.ctc_kernel_size,
-                      &h->ctc_blocks[i]))
-        return bail(1);
-  }
+  if (!ok) return 1;
   // FFT twiddles exp(-2 pi i m / 1024), rounded once from double
   std::vector<float2> tw(c.n_dft);
   for (int m = 0; m < c.n_dft; ++m) {
@@ -415,8 +392,8 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
       cudaMalloc(&h->mel_wc, sizeof(float) * wc.size()) != cudaSuccess ||
       cudaMemcpy(h->mel_off, off.data(), sizeof(int) * (c.n_mels + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(h->mel_wc, wc.data(), sizeof(float) * wc.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: device allocation of the mel tables failed");
-    return bail(1);
+    snprintf(g_errbuf, sizeof(g_errbuf), "engine: device allocation of the mel tables failed");
+    return 1;
   }
   if (cudaMalloc(&h->twiddle, sizeof(float2) * c.n_dft) != cudaSuccess ||
       cudaMalloc(&h->mel_lo, sizeof(int) * c.n_mels) != cudaSuccess ||
@@ -424,13 +401,69 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
       cudaMemcpy(h->twiddle, tw.data(), sizeof(float2) * c.n_dft, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(h->mel_lo, lo.data(), sizeof(int) * c.n_mels, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(h->mel_hi, hi.data(), sizeof(int) * c.n_mels, cudaMemcpyHostToDevice) != cudaSuccess) {
-    snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: device allocation of frontend tables failed");
-    return bail(1);
+    snprintf(g_errbuf, sizeof(g_errbuf), "engine: device allocation of frontend tables failed");
+    return 1;
   }
-  if (tc_init(&h->tc) != 0) return bail(1);
+  if (tc_init(&h->tc) != 0) return 1;
   if (const char* e = getenv("B200ASR_NO_CHAIN")) h->use_chain = !(e[0] == '1');
   if (const char* e = getenv("B200ASR_NO_PDL")) g_pdl_enabled = !(e[0] == '1');
   if (const char* e = getenv("B200ASR_NO_PAIR")) h->use_pair = !(e[0] == '1');
+  return 0;
+}
+
+}  // namespace b200asr
+
+// ================================================================================================== C ABI
+extern "C" {
+
+B200ASR_API int b200asr_abi_version(void) { return B200ASR_ABI_VERSION; }
+
+B200ASR_API const char* b200asr_last_error(b200asr_handle h) { return h ? h->err.c_str() : g_errbuf; }
+
+B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const b200asr_config* cfg, int device, b200asr_handle* out) {
+  if (!weight_blob || !cfg || !out) return fail(nullptr, "b200asr_create: null argument");
+  if (cfg->abi_version != B200ASR_ABI_VERSION) return fail(nullptr, "b200asr_create: ABI version mismatch");
+  *out = nullptr;
+  b200asr_engine* h = nullptr;
+  if (b200asr::engine_alloc(weight_blob, blob_bytes, device, "b200asr_create", &h)) return 1;
+  h->cfg = *cfg;
+  auto bail = [&](int) {
+    std::string e = g_errbuf;
+    b200asr_destroy(h);
+    snprintf(g_errbuf, sizeof(g_errbuf), "%s", e.c_str());
+    return 1;
+  };
+  const b200asr_config& c = h->cfg;
+  if (c.n_dft != 1024) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: n_dft must be 1024 (reference hard-codes it)"); return bail(1); }
+  if (c.dmodel % 16 != 0 || c.dmodel > 512) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: dmodel must be a multiple of 16, <= 512"); return bail(1); }
+  const int D = c.dmodel;
+  h->F1 = same_pad(c.n_mels, 3, 2).out;
+  h->F2 = same_pad(h->F1, 3, 2).out;
+  bool ok = true;
+  h->c1w = lookup(h, "sub.conv1.w", 9ull * D, &ok);
+  h->c1b = ok ? lookup(h, "sub.conv1.b", D, &ok) : nullptr;
+  h->c2w = ok ? lookup(h, "sub.conv2.w", 9ull * D * D, &ok) : nullptr;
+  h->c2b = ok ? lookup(h, "sub.conv2.b", D, &ok) : nullptr;
+  h->linw = ok ? lookup(h, "sub.lin.w", (uint64_t)h->F2 * D * D, &ok) : nullptr;
+  h->linb = ok ? lookup(h, "sub.lin.b", D, &ok) : nullptr;
+  if (!ok) return bail(1);
+  h->enc_blocks.resize(c.num_blocks);
+  for (int i = 0; i < c.num_blocks; ++i)
+    if (!load_block(h, "enc." + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.kernel_size, &h->enc_blocks[i]))
+      return bail(1);
+  if (c.vocab > 0) {
+    h->ctc_projw = lookup(h, "ctc.proj.w", (uint64_t)D * D, &ok);
+    h->ctc_projb = ok ? lookup(h, "ctc.proj.b", D, &ok) : nullptr;
+    h->ctc_fcw = ok ? lookup(h, "ctc.fc.w", (uint64_t)c.vocab * D, &ok) : nullptr;
+    h->ctc_fcb = ok ? lookup(h, "ctc.fc.b", c.vocab, &ok) : nullptr;
+    if (!ok) return bail(1);
+    h->ctc_blocks.resize(c.ctc_blocks);
+    for (int i = 0; i < c.ctc_blocks; ++i)
+      if (!load_block(h, "ctc.blk" + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.ctc_kernel_size,
+                      &h->ctc_blocks[i]))
+        return bail(1);
+  }
+  if (b200asr::engine_init_frontend(h, weight_blob)) return bail(1);
   {
     ConvSubParams probe{};
     probe.D = D; probe.F2 = h->F2; probe.B = 1; probe.T = 1; probe.w2 = h->c2w;
@@ -446,6 +479,7 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->chunk) b200asr::chunk_model_free(h->chunk);
   if (h->stage_wav) cudaFree(h->stage_wav);
   if (h->blob_dev) cudaFree(h->blob_dev);
   if (h->twiddle) cudaFree(h->twiddle);

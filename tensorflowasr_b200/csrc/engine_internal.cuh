@@ -26,7 +26,7 @@ struct BlobEntry {
 
 struct LNW { const float *g, *b; };
 struct FFNW { LNW ln; const float *w1, *b1, *w2, *b2; };
-struct MHSAW { LNW ln; const float *wqkv, *wo, *bo; };
+struct MHSAW { LNW ln; const float *wqkv, *wo, *bo; const float* bqkv = nullptr; /* Keras MultiHeadAttention q/k/v biases (ChunkConformer) */ };
 struct ConvW { LNW ln; const float *pw1w, *pw1b, *dww, *pww, *pwb, *pw2w, *pw2b; };
 struct BlockW { FFNW ffn1, ffn2; MHSAW mhsa; ConvW conv; LNW ln; int kernel_size; };
 
@@ -50,6 +50,13 @@ struct GraphEntry {
 };
 
 }  // namespace
+
+namespace b200asr {
+struct ChunkModel;                                  // chunk_engine.cu: ChunkConformer weights + geometry
+void chunk_model_free(ChunkModel* m);
+int engine_alloc(const void* weight_blob, size_t blob_bytes, int device, const char* who, b200asr_engine** out);   // engine.cu
+int engine_init_frontend(b200asr_engine* h, const void* weight_blob);                                            // engine.cu
+}
 
 struct b200asr_engine {
   b200asr_config cfg;
@@ -93,6 +100,7 @@ struct b200asr_engine {
   } pipe[2];
   cudaStream_t pipe_copy = nullptr, pipe_compute = nullptr;
   // b200asr_debug_encode_taps: when set, run_encoder copies the residual stream after the subsampler and after every block
+  b200asr::ChunkModel* chunk = nullptr;   // set by b200asr_chunk_create: this handle is a ChunkConformer (state-cache streaming) engine
   float* tap_dst = nullptr;
   int tap_count = 0, tap_max = 0;
 };
@@ -169,6 +177,10 @@ bool load_block(b200asr_handle h, const std::string& p, int D, int F, int H, int
   w->mhsa.wqkv = L("mhsa.wqkv", 3ull * H * dh * uD);
   w->mhsa.wo = L("mhsa.wo", uD * H * dh);
   w->mhsa.bo = L("mhsa.bo", uD);
+  {
+    auto it = h->tensors.find(p + "mhsa.bqkv");
+    w->mhsa.bqkv = (it != h->tensors.end() && it->second.second == 3ull * H * dh) ? it->second.first : nullptr;
+  }
   w->conv.ln.g = L("conv.ln.g", uD);
   w->conv.ln.b = L("conv.ln.b", uD);
   w->conv.pw1w = L("conv.pw1.w", 2 * uD * uD);

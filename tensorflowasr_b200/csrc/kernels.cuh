@@ -122,4 +122,45 @@ struct BeamParams {
 size_t beam_workspace_bytes(int B, int T, int beam);
 int launch_ctc_beam(const BeamParams& p, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------- chunk_ops.cu
+// ChunkConformer state-cache streaming helpers (see the file header for the cache representation).
+int launch_stream_wav_shift(float* wavbuf /*[B, 2S]*/, const float* chunk /*[B, S]*/, int B, int S, cudaStream_t stream);
+int launch_stream_mel_cat(float* melcat /*[B, sub+n, F]*/, float* sub_cache /*[B, sub, F]*/, const float* mel_new /*[B, n, F]*/, int B, int sub,
+                          int n, int F, cudaStream_t stream);
+int launch_rows_cat(const float* a, int na, const float* b, int nb, float* out, int B, int D, cudaStream_t stream);
+int launch_rows_slice(const float* src, int T, int t0, int n, float* dst, int B, int D, cudaStream_t stream);
+struct CacheUpdateParams {
+  const float* old_cache;   // [B, W, C]
+  const float* cur;         // [B*Tc rows, cur_ld], columns [cur_col0, cur_col0 + C)
+  float* new_cache;         // [B, W, C]
+  int B, W, C, Tc, shift, cur_ld, cur_col0;   // shift = Tc - win_back
+};
+int launch_stream_cache_update(const CacheUpdateParams& p, cudaStream_t stream);
+struct StreamAttnParams {
+  const float* qkv;        // [B*Tc, 3*H*dh] new rows: q | k | v (q pre-scaled, biases added)
+  const float* kv_cache;   // [B, W, 2*H*dh] right-aligned; the last c rows are valid
+  float* out;              // [B*Tc, H*dh]
+  int B, Tc, H, dh, W, c, win_front, win_back, round_tf32;
+};
+int launch_stream_attention(const StreamAttnParams& p, cudaStream_t stream);
+struct StreamDwParams {
+  const float* cache;   // [B, K-1, D] GLU rows of the previous frames (zeros = 'causal' padding)
+  const float* cur;     // [B*Tc, D]
+  const float* w;       // [K, D]
+  float* y;             // [B*Tc, D]
+  int B, Tc, D, K, round_tf32;
+};
+int launch_stream_dwconv(const StreamDwParams& p, cudaStream_t stream);
+struct PickParams {
+  const float* hidden;   // [B, T, D]
+  const float* logits;   // [B, T, ldv] (first V columns are classes)
+  float* feats;          // [B, T, D] out: kept rows first, zero rows behind
+  float* picked;         // [B, T, V] out (nullable): the kept rows' logits
+  int* counts;           // [B] out
+  int* n_max;            // [1] out: max over the batch
+  int B, T, D, V, ldv, blank;
+};
+int launch_feature_pick(const PickParams& p, cudaStream_t stream);
+int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t stream);
+
 }  // namespace b200asr

@@ -129,3 +129,28 @@ def test_warp_fft_phases_on_host(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "max_rel_err" in r.stdout
+
+
+def test_chunk_weight_packing_layout():
+    """ChunkConformer blob: K-major GEMM operands, q/k/v biases concatenated with 1/sqrt(dh) folded into the q part, heads padded to a
+    multiple of 4 classes with a never-winning bias, every tensor-core operand an exact tf32 number."""
+    from tensorflowasr_b200 import chunk_model as CM
+    _, fe_raw, _, _ = W.random_model(0, num_blocks=1)
+    geo = CM.ChunkGeometry(enc_blocks=2, helper_blocks=1, txt_classes=33)
+    raw = CM.random_chunk_weights(3, fe_raw, geo)
+    dev = CM.chunk_device_tensors(raw, geo)
+    D, H, dh = geo.dmodel, geo.num_heads, geo.head_size
+    assert dev["enc.1.mhsa.wqkv"].shape == (3 * H * dh, D) and dev["enc.1.mhsa.bqkv"].shape == (3 * H * dh,)
+    np.testing.assert_allclose(dev["enc.0.mhsa.bqkv"][:H * dh], raw["enc.0.mhsa.bq"].reshape(-1) / np.sqrt(np.float32(dh)), rtol=1e-6)
+    np.testing.assert_array_equal(dev["enc.0.mhsa.bqkv"][H * dh:2 * H * dh], raw["enc.0.mhsa.bk"].reshape(-1))
+    # row h*dh + o of the q block = column (h, o) of the Keras kernel [D, H, dh], scaled
+    want = raw["helper.0.mhsa.wq"][:, 2, 5] / np.sqrt(np.float32(dh))
+    np.testing.assert_allclose(dev["helper.0.mhsa.wqkv"][2 * dh + 5], want, rtol=2e-3, atol=1e-6)
+    assert dev["dec.fc.w"].shape == (36, D) and dev["dec.fc.b"].shape == (36,) and (dev["dec.fc.b"][33:] < -1e29).all()
+    assert (dev["dec.fc.w"][33:] == 0).all() and dev["picker.fc.w"].shape == (280, D)
+    for k in ("enc.0.ffn1.w1", "sub.conv2.w", "dec.fc.w", "picker.proj.w", "enc.1.mhsa.wqkv"):
+        assert (dev[k].view(np.uint32) & 0x1FFF).max() == 0, k                   # exact tf32 numbers
+    assert (dev["enc.0.conv.dw.w"].view(np.uint32) & 0x1FFF).max() != 0         # CUDA-core operands stay fp32
+    blob = CM.pack_chunk_blob(raw, geo)
+    assert blob[:8] == b"B2ASRW01"
+    assert ctypes.sizeof(CM.ChunkConfig) == 4 * 22 + 4 * 8
