@@ -119,7 +119,9 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows) {
 
 __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would strip the address space and turn every
+  // access through a derived pointer into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* Qs = smem;                                  // 2 slabs x 128 rows x 128 B = 32 KB
   uint8_t* Ks = Qs + 2 * kQT * 128;                    // 2 slabs x 256 rows x 128 B = 64 KB
   uint8_t* Vt = Ks + 2 * kKT * 128;                    // 8 slabs x  64 rows x 128 B = 64 KB   (V transposed: rows = head dim)

@@ -54,6 +54,25 @@ __device__ __forceinline__ float2 relu_rn2(unsigned long long v) {
   return make_float2(__uint_as_float(tf32_rn_bits(lo)), __uint_as_float(tf32_rn_bits(hi)));
 }
 
+// explicit shared-window accesses: pointers carved out of the dynamic shared-memory block with run-time offsets lose their address
+// space, and the compiler then emits generic LD / ST (measured: the first version of this kernel ran 3x slower than planned)
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
+  unsigned long long v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_v2(uint32_t saddr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
 template <int BLOCK_N>
 __host__ __device__ constexpr int cs_stages() { return BLOCK_N <= 160 ? 4 : 3; }
 
@@ -65,7 +84,9 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
   constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 4;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr int kStg = cs_stages<BLOCK_N>();
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would strip the address space and turn every
+  // access through a derived pointer into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   float* wsm = reinterpret_cast<float*>(smem + kStg * kStageBytes);                  // epilogue transpose scratch (4 warps)
   float* w1s = wsm + 4 * kWsmFloats;                                                 // conv1 weights [9][D] + bias [D]
   float2* patch = reinterpret_cast<float2*>(w1s + 10 * p.D);                         // [bt][7][PW] of (m, m)
@@ -175,24 +196,29 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
     const int col_shift = 2 * p.pf2 + p.pf1;      // patch column pc <-> mel column pc - col_shift
     const int row_shift = 2 * p.pt2 + p.pt1;      // patch row pr of time row (b, t2) <-> mel row 4 t2 - row_shift + pr
     const int total_trows = p.B * p.T2;
+    const uint32_t patch_s = smem_u32(patch), w1s_s = smem_u32(w1s), smem_s = smem_u32(smem);
     pdl_wait();                                   // mel (written by the frontend kernel) is complete and visible
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      // ---- stage the mel patch of this tile's time rows
+      // ---- stage the mel patch of this tile's time rows: one warp per (time row, patch row), lanes over the columns (no divisions,
+      // independent loads)
       asm volatile("bar.sync 3, %0;" ::"n"(kProdThreads) : "memory");        // every producer is done with the previous patch
       const int per_row = kPatchRows * PW;
-      for (int idx = pt; idx < p.bt * per_row; idx += kProdThreads) {
-        const int i = idx / per_row, rem = idx - i * per_row;
-        const int pr = rem / PW, pc = rem - pr * PW;
+      const int pwarp = pt >> 5;
+      for (int rr = pwarp; rr < p.bt * kPatchRows; rr += kProdWarps) {
+        const int i = rr / kPatchRows, pr = rr - i * kPatchRows;
         const int g = tile * p.bt + i;
-        float v = 0.f;
-        if (g < total_trows) {
-          const int b = g / p.T2, t2 = g - b * p.T2;
-          const int t = 4 * t2 - row_shift + pr, f = pc - col_shift;
-          if (t >= 0 && t < p.T && f >= 0 && f < p.F) v = __ldg(p.mel + ((size_t)b * p.T + t) * p.F + f);
+        const bool gv = g < total_trows;
+        const int b = gv ? g / p.T2 : 0, t2 = gv ? g - b * p.T2 : 0;
+        const int t = 4 * t2 - row_shift + pr;
+        const bool tv = gv && t >= 0 && t < p.T;
+        const float* mrow = p.mel + ((size_t)b * p.T + (tv ? t : 0)) * p.F;
+        for (int pc = lane; pc < PW; pc += 32) {
+          const int f = pc - col_shift;
+          const float v = (tv && f >= 0 && f < p.F) ? __ldg(mrow + f) : 0.f;
+          sts_v2(patch_s + (uint32_t)(rr * PW + pc) * 8u, v, v);
         }
-        patch[idx] = make_float2(v, v);
       }
       asm volatile("bar.sync 3, %0;" ::"n"(kProdThreads) : "memory");
       // ---- per-pass row geometry (fixed for the tile)
@@ -222,27 +248,27 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
         const bool cvalid = c0 < p.D;             // D % 8 == 0: the 8 channels are valid together
         unsigned long long w[9][4], bias[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          bias[q] = cvalid ? pack2(w1s[9 * p.D + c0 + 2 * q], w1s[9 * p.D + c0 + 2 * q + 1]) : 0ull;
+        for (int q = 0; q < 4; ++q) {      // (c0 is even and w1s is 8-byte aligned: one 64-bit shared load per pair)
+          bias[q] = cvalid ? lds_u64(w1s_s + (uint32_t)(9 * p.D + c0 + 2 * q) * 4u) : 0ull;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) w[t][q] = cvalid ? pack2(w1s[t * p.D + c0 + 2 * q], w1s[t * p.D + c0 + 2 * q + 1]) : 0ull;
+          for (int t = 0; t < 9; ++t) w[t][q] = cvalid ? lds_u64(w1s_s + (uint32_t)(t * p.D + c0 + 2 * q) * 4u) : 0ull;
         }
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap - kh * 3;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
+          const uint32_t sa = smem_s + (uint32_t)stage * kStageBytes;
 #pragma unroll
           for (int ps = 0; ps < 2; ++ps) {
             const int r = ps * 64 + rsub;
             float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
             if (rvalid[ps] && cvalid && ((vt[ps] >> kh) & 1) && ((vf[ps] >> kw) & 1)) {
               unsigned long long a0 = bias[0], a1 = bias[1], a2 = bias[2], a3 = bias[3];
-              const unsigned long long* pp = reinterpret_cast<const unsigned long long*>(patch) + pbase[ps] + (2 * kh) * PW + 2 * kw;
+              const uint32_t pp = patch_s + (uint32_t)(pbase[ps] + (2 * kh) * PW + 2 * kw) * 8u;
 #pragma unroll
               for (int a = 0; a < 3; ++a) {
 #pragma unroll
                 for (int bc = 0; bc < 3; ++bc) {
-                  const unsigned long long m = pp[a * PW + bc];
+                  const unsigned long long m = lds_u64(pp + (uint32_t)(a * PW + bc) * 8u);
                   a0 = cs_ffma2(m, w[a * 3 + bc][0], a0);
                   a1 = cs_ffma2(m, w[a * 3 + bc][1], a1);
                   a2 = cs_ffma2(m, w[a * 3 + bc][2], a2);
@@ -254,9 +280,9 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
               o1 = make_float4(r2.x, r2.y, r3.x, r3.y);
             }
             // K-major SWIZZLE_128B: 16-byte chunk q of row r lives at r * 128 + ((q ^ (r & 7)) << 4)
-            uint8_t* rowp = sa + r * 128;
-            *reinterpret_cast<float4*>(rowp + (((2 * cg) ^ (r & 7)) << 4)) = o0;
-            *reinterpret_cast<float4*>(rowp + (((2 * cg + 1) ^ (r & 7)) << 4)) = o1;
+            const uint32_t rowp = sa + (uint32_t)r * 128u;
+            sts_v4(rowp + (uint32_t)((((2 * cg) ^ (r & 7))) << 4), o0);
+            sts_v4(rowp + (uint32_t)((((2 * cg + 1) ^ (r & 7))) << 4), o1);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
           __syncwarp();

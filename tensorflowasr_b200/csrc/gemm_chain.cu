@@ -44,7 +44,9 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   constexpr uint32_t kRing = (CH > N2 ? CH : N2) * 128;               // one weight slab: rows x 32 floats
   constexpr int KB2 = (CH + 31) / 32;                                 // W2 slabs per chunk
   constexpr int KSTEPS2 = CH / 8;                                     // k-steps of the second GEMM per chunk
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would strip the address space and turn every
+  // access through a derived pointer into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* xs = smem;                                                 // kb1 slabs
   uint8_t* ring = xs + (size_t)p.kb1 * kXSlab;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * kRing);
@@ -58,7 +60,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* acc2_empty = acc2_full + 1;
   uint64_t* r_full = acc2_empty + 1;     // residual tile landed in the (recycled) X slabs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 1);
-  float* statbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [128][2][4] LN partial sums
+  float* statbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + (((2 * STAGES + 9) * 8 + 4 + 15) / 16) * 16);   // [128][2][4] LN partial sums (16-byte aligned: bars sit on a 1024-byte boundary)
   float* pcache = statbuf + 128 * 2 * 4;                      // bias1[N1] | bias2 | ln1_g | ln1_b | ln2_g | ln2_b  (N2 each)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -55,7 +55,9 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                        const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_r,
                        const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would strip the address space and turn every
+  // access through a derived pointer into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* xs = smem;                                    // X: kSlabs x 16 KB; later [0,40K) residual/output tile, [40K,80K) peer partial
   uint8_t* xchg = xs + kSlabs * kHSlab;                  // 64-row tile written by the peer CTA
   uint8_t* ring = xs + (size_t)kSlabs * kXSlab;
@@ -71,7 +73,7 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   uint64_t* xchg_ready = r_full + 1;
   uint64_t* xchg_full = xchg_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xchg_full + 1);
-  float* statbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [64][2][4]
+  float* statbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + (((2 * STAGES + 10) * 8 + 4 + 15) / 16) * 16);   // [64][2][4] (16-byte aligned: bars sit on a 1024-byte boundary)
   float* pcache = statbuf + HR * 2 * 4;                  // bias1 (local chunks) | bias2 | ln1_g | ln1_b | ln2_g | ln2_b
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -50,7 +50,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int kStages = stages_for(kIsLN, BLOCK_N, BLOCK_M);
   constexpr int kNSlab = (BLOCK_N + 31) / 32;
   constexpr uint32_t kStageTile = kIsLN ? (uint32_t)BLOCK_M * kNSlab * 128 : 0;   // LN epilogues: residual-in / output staging tile
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would strip the address space and turn every
+  // access through a derived pointer into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* stile = smem + kStages * kStageBytes;          // (LN epilogues) [BLOCK_M rows x kNSlab slabs of 32 columns], SW128
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stile + kStageTile);
   uint64_t* empty_bar = full_bar + kStages;

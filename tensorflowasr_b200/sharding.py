@@ -1,9 +1,9 @@
 """Utterance sharding across the GPUs of one box: one process per GPU, full weight replica, contiguous
-split of the batch, and ONE exchange per batch -- an all_gather of the decoded token ids + lengths (NCCL on GPUs, gloo
+split of the batch, and ONE exchange per batch -- a single all_gather of the decoded token ids + lengths (NCCL on GPUs, gloo
 in the CPU tests).  No tensor / sequence parallelism: d_model is 144."""
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 
 def shard_range(num_utts: int, rank: int, world: int) -> Tuple[int, int]:
@@ -13,9 +13,64 @@ def shard_range(num_utts: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+class IdsExchange:
+    """One collective per batch.  ids [B, T] and lens [B] of a rank live back to back in ONE flat int32 buffer, so the decoder
+    writes them where the collective reads them (no packing kernels) and a single `all_gather_into_tensor` moves both.  The
+    collective is issued asynchronously: NCCL's stream waits for the producing stream, the producing stream does NOT wait for NCCL,
+    so the next batch's kernels launch immediately and the exchange overlaps them.  `slots` buffers rotate; a slot is waited for
+    before it is handed out again.  Every rank must use the same (B, T)."""
+
+    def __init__(self, B: int, T: int, device, group=None, slots: int = 2):
+        import torch
+        import torch.distributed as dist
+        self.B, self.T, self.group = B, T, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = B * T + B
+        self.flat = [torch.full((n,), -1, device=device, dtype=torch.int32) for _ in range(slots)]
+        # (world == 1: `gathered` aliases the slot)
+        self.gathered = [torch.empty((self.world * n,), device=device, dtype=torch.int32) if self.world > 1 else f for f in self.flat]
+        self.gathered = list(self.gathered)
+        self.work: List[Optional[object]] = [None] * slots
+        self._next = 0
+
+    def acquire(self) -> int:
+        """Next slot; blocks the CURRENT STREAM (not the host) until that slot's previous collective has finished."""
+        s = self._next
+        self._next = (self._next + 1) % len(self.flat)
+        if self.work[s] is not None:
+            self.work[s].wait()
+            self.work[s] = None
+        return s
+
+    def buffers(self, slot: int):
+        """(ids [B, T], lens [B]) views of the slot's flat buffer: hand these to Engine.recognize."""
+        n = self.B * self.T
+        return self.flat[slot][:n].view(self.B, self.T), self.flat[slot][n:]
+
+    def gather(self, slot: int):
+        """Issue the slot's all_gather (async).  Call on the stream that produced the slot's contents."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return                                   # a single rank already holds everything: result() hands back the slot itself
+        self.work[slot] = dist.all_gather_into_tensor(self.gathered[slot], self.flat[slot], group=self.group, async_op=True)
+
+    def result(self, slot: int):
+        """(ids [world * B, T], lens [world * B]) of the slot, after making the current stream wait for its collective."""
+        import torch
+        if self.work[slot] is not None:
+            self.work[slot].wait()
+            self.work[slot] = None
+        n = self.B * self.T
+        if self.world == 1:
+            return self.buffers(slot)
+        g = self.gathered[slot].view(self.world, n + self.B)
+        return g[:, :n].reshape(self.world * self.B, self.T), g[:, n:].reshape(self.world * self.B)
+
+
 def gather_ids(ids, lens, group=None):
     """ids [B_local, T] int32 (-1 padded), lens [B_local] -> (ids [B_total, T_max], lens [B_total]) on every rank.
-    Ranks may hold different B_local and T (ragged shards are padded to the group maximum before the collective)."""
+    Ranks may hold different B_local and T: one small all_gather of the shapes, then ONE all_gather of a packed buffer
+    (length in column 0, ids behind it) padded to the group maximum."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -24,17 +79,21 @@ def gather_ids(ids, lens, group=None):
     dist.all_gather(shapes, shape, group=group)
     bmax = max(int(s[0]) for s in shapes)
     tmax = max(int(s[1]) for s in shapes)
-    pad = torch.full((bmax, tmax), -1, device=ids.device, dtype=torch.int32)
-    pad[:ids.shape[0], :ids.shape[1]] = ids
-    lpad = torch.zeros((bmax,), device=ids.device, dtype=torch.int32)
-    lpad[:lens.shape[0]] = lens
-    all_ids = [torch.empty_like(pad) for _ in range(world)]
-    all_lens = [torch.empty_like(lpad) for _ in range(world)]
-    dist.all_gather(all_ids, pad, group=group)
-    dist.all_gather(all_lens, lpad, group=group)
-    out_ids = torch.cat([a[:int(s[0])] for a, s in zip(all_ids, shapes)], dim=0)
-    out_lens = torch.cat([l[:int(s[0])] for l, s in zip(all_lens, shapes)], dim=0)
-    return out_ids, out_lens
+    packed = torch.full((bmax, tmax + 1), -1, device=ids.device, dtype=torch.int32)
+    packed[:, 0] = 0
+    packed[:lens.shape[0], 0] = lens
+    packed[:ids.shape[0], 1:ids.shape[1] + 1] = ids
+    out = torch.empty((world * bmax, tmax + 1), device=ids.device, dtype=torch.int32)
+    if hasattr(dist, "all_gather_into_tensor") and ids.device.type == "cuda":
+        dist.all_gather_into_tensor(out, packed, group=group)
+    else:                                            # gloo (CPU tests) has no all_gather_into_tensor
+        parts = [torch.empty_like(packed) for _ in range(world)]
+        dist.all_gather(parts, packed, group=group)
+        out = torch.cat(parts, dim=0)
+    out = out.view(world, bmax, tmax + 1)
+    rows = [out[r, :int(s[0])] for r, s in enumerate(shapes)]
+    allp = torch.cat(rows, dim=0)
+    return allp[:, 1:].contiguous(), allp[:, 0].contiguous()
 
 
 def recognize_sharded(engine, wavs, group=None):

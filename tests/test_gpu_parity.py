@@ -5,7 +5,7 @@ from the reference itself.
 Tolerances (stated per north_star "within a stated fp32 tolerance"):
   * fp32 mode (CUDA-core GEMMs): |enc - oracle| <= 2e-4, |logits - oracle| <= 2e-3 (values up to ~30)
   * tf32 mode (tcgen05 tensor cores, fp32 accumulate, every operand rounded to nearest tf32 by its producer):
-    |enc - oracle| <= 8e-3; logits rms <= 1e-2 and max <= 0.15 (the max is an outlier bound, see tests/conftest.py)
+    |enc - oracle| <= 8e-3; logits rms <= 1e-2 and max <= 0.25 (the max is an outlier bound, see tests/conftest.py)
   * mel (always fp32): 5e-3 dB on a [-80, 0] scale
   * token ids (greedy, beam): bit-exact
 """

@@ -8,7 +8,7 @@ equal-length batches), then asserts
   * greedy token ids identical row by row -- noise rows included, in BOTH precision modes (the tf32 mode is the benchmarked one);
     in tf32 mode a frame may flip only if the reference itself decides it by less than twice the stated tolerance
     (conftest.assert_ids_match; the flips are counted and printed);
-  * logits within the stated tolerances (conftest.py: fp32 mode max 2e-3; tf32 mode rms 1e-2, max 0.15 -- the reference's CTC
+  * logits within the stated tolerances (conftest.py: fp32 mode max 2e-3; tf32 mode rms 1e-2, max 0.25 -- the reference's CTC
     decoder amplifies a 1e-3 encoder perturbation up to 100x on single elements, see profiles/r02_stage_errors.md);
   * config 5: the beam-16 hypotheses of the device decoder equal the reference C++ decoder's on the same probabilities.
 """
