@@ -65,7 +65,9 @@ typedef struct {
   int32_t chunk_samples;
   int32_t precision;          /* B200ASR_PRECISION_* */
   int32_t use_cuda_graph;     /* 1 = capture each (shape, pointer set) once and replay */
-  int32_t reserved[8];
+  /* translator (pinyin ids + encoder states -> characters, conformer_blocks.py:504-552); tr_blocks = 0: no translator in the blob */
+  int32_t tr_blocks, tr_kernel_size, tr_inp_classes, tr_vocab;
+  int32_t reserved[4];
 } b200asr_config;
 
 /* Weight blob: produced by tensorflowasr_b200.weights.pack_for_device() (see weights.py for the tensor list).
@@ -97,6 +99,13 @@ B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, co
 B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V,
                      int blank, int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev,
                      float* scores_dev, void* stream);
+
+/* Translator session Run: "inputs" int32 [B,U] (greedy phone ids, zero padded: the deployment appends ten zeros), "enc" f32 [B,T',D]
+ * -> "Identity:0" f32 [B,U,tr_vocab]   (Inference/CppInference/onnx/src/core/asr_session.cpp:125-150, PythonInference asr.py:77-83).
+ * Embedding -> RBlocks (FFModule, cross attention of LN(x + sinusoidal positions) over the encoder states, ConvModule, FFModule, LN)
+ * -> Dense. */
+B200ASR_API int b200asr_translate(b200asr_handle h, const int32_t* ids_dev /*[B,U]*/, const float* enc_dev /*[B,T',D]*/, int B, int U, int Tp,
+                                  float* logits_dev /*[B,U,tr_vocab]*/, void* stream);
 
 /* wav -> greedy token ids in one call, device buffers. */
 B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev /*[B,T']*/,

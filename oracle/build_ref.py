@@ -3,7 +3,7 @@
 Run in the build container, where /root/reference exists; the GPU box only uses the staged results.
   * libonnxruntime.so.1.10.0  : the reference's vendored ONNX Runtime (binary, copied as is)
   * libortref.so              : oracle/ort_ref.cpp compiled against the vendored ORT headers
-  * models/{offline,streaming}/{encoder,ctc_model}.onnx : the reference's shipped weights (binary, copied as is)
+  * models/{offline,streaming}/{encoder,ctc_model,translator}.onnx : the reference's shipped weights (binary, copied as is)
   * libctcdec_ref.so          : the reference's externals/ctc_decoders C++ (beam/greedy), compiled from the zip where it
                                 lies with the stub headers in oracle/ctcdec_stubs/ (openfst/kenlm are not vendored and
                                 the ext_scorer == nullptr path never touches them) + oracle/ctcdec_wrap.cpp
@@ -46,9 +46,9 @@ def build(verbose: bool = False) -> bool:
               "-Wl,-rpath,$ORIGIN"])
     for kind in ("offline", "streaming"):
         os.makedirs(os.path.join(REF, "models", kind), exist_ok=True)
-        for m in ("encoder.onnx", "ctc_model.onnx"):
+        for m in ("encoder.onnx", "ctc_model.onnx", "translator.onnx"):
             dst = os.path.join(REF, "models", kind, m)
-            if not os.path.isfile(dst):
+            if not os.path.isfile(dst) and os.path.isfile(os.path.join(MODELS, kind, m)):
                 shutil.copyfile(os.path.join(MODELS, kind, m), dst)
     # vocabulary files used by the reference's TextFeaturizer
     os.makedirs(os.path.join(REF, "dict"), exist_ok=True)

@@ -253,3 +253,53 @@ def streaming_encoder_forward(wav: np.ndarray, raw: Raw, num_blocks: int, chunk:
     x = np.pad(wav, ((0, 0), (0, n * chunk - L))).reshape(B * n, chunk)
     enc = encoder_forward(x, raw, num_blocks, dtype=dtype)
     return enc.reshape(B, n * enc.shape[1], enc.shape[2])
+
+
+# ----------------------------------------------------------------------------------------------------- translator
+def positional_encoding(max_len: int, size: int, dtype=np.float64) -> np.ndarray:
+    """positional_encoding (asr/models/layers/positional_encoding.py:19-36): sin on the even columns, cos on the odd columns,
+    both with the exponent 2 * (index // 2) / size.  -> [max_len, size]."""
+    pos = np.arange(max_len, dtype=np.float32)[:, None]
+    index = np.arange(size, dtype=np.float32)[None, :]
+    pe = pos * (np.float32(1.0) / np.power(np.float32(10000.0), (2 * (index // 2)) / np.float32(size)))
+    out = np.zeros((max_len, size), dtype=np.float32)
+    out[:, 0::2] = np.sin(pe[:, 0::2])
+    out[:, 1::2] = np.cos(pe[:, 1::2])
+    return out.astype(dtype)
+
+
+def rmhsa_module(x, enc, raw: Raw, p: str):
+    """RMHSAModule.call (conformer_blocks.py:454-463): queries = LN(x + positional encoding), keys = values = the encoder states
+    (no LayerNorm, no positional term on them), residual on x (without the positional encoding)."""
+    dt = x.dtype
+    q_in = layer_norm(x + positional_encoding(x.shape[1], x.shape[2], dt)[None], raw[p + ".ln.g"].astype(dt), raw[p + ".ln.b"].astype(dt))
+    wq, wk, wv, wo = (raw[p + s].astype(dt) for s in (".wq", ".wk", ".wv", ".wo"))
+    q = np.einsum("bni,hio->bnho", q_in, wq) / np.sqrt(np.asarray(wq.shape[-1], dtype=dt))
+    k = np.einsum("bmi,hio->bmho", enc, wk)
+    v = np.einsum("bmi,hio->bmho", enc, wv)
+    logits = np.einsum("bnho,bmho->bhnm", q, k)
+    logits = logits - logits.max(-1, keepdims=True)
+    e = np.exp(logits)
+    coef = e / e.sum(-1, keepdims=True)
+    o = np.einsum("bhnm,bmhi->bnhi", coef, v)
+    return x + np.einsum("bnhi,hio->bno", o, wo) + raw[p + ".bo"].astype(dt)
+
+
+def rblock(x, enc, raw: Raw, p: str):
+    """RBlock.call (conformer_blocks.py:496-502)."""
+    x = ff_module(x, raw, p + "ffn1")
+    x = rmhsa_module(x, enc, raw, p + "mhsa")
+    x = conv_module(x, raw, p + "conv")
+    x = ff_module(x, raw, p + "ffn2")
+    dt = x.dtype
+    return layer_norm(x, raw[p + "ln.g"].astype(dt), raw[p + "ln.b"].astype(dt))
+
+
+def translator_forward(ids: np.ndarray, enc: np.ndarray, raw: Raw, num_blocks: int, dtype=np.float64) -> np.ndarray:
+    """Translator.call (conformer_blocks.py:546-552): embedding -> N x RBlock(x, enc) -> Dense.  ids [B, U] int, enc [B, T', D]
+    -> [B, U, tar_classes]."""
+    x = np.asarray(raw["tr.emb"], dtype=dtype)[np.asarray(ids)]
+    enc = np.asarray(enc, dtype=dtype)
+    for i in range(num_blocks):
+        x = rblock(x, enc, raw, f"tr.{i}.")
+    return x @ raw["tr.fc.w"].astype(dtype) + raw["tr.fc.b"].astype(dtype)

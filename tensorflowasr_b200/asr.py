@@ -164,7 +164,8 @@ class ASR:
 
     # ------------------------------------------------------------------ model loading
     def compile(self, path: str):
-        """`path` holds encoder.onnx + ctc_model.onnx exactly as the reference's deployment directory does."""
+        """`path` holds encoder.onnx + ctc_model.onnx (+ translator.onnx) exactly as the reference's deployment directory does
+        (asr.py:22-25)."""
         chunk = self.chunk if self.speech_config["streaming"] else 0
         self.engine = E.engine_from_onnx(path, device=self.device, precision=self.precision, chunk_samples=chunk)
         mc = self.model_config or {}
@@ -210,29 +211,70 @@ class ASR:
         ids, lens = self.engine.ctc_greedy(logits, blank=blank)
         return ids[0, :int(lens[0])].cpu().tolist()
 
+    def has_translator(self) -> bool:
+        return self.engine is not None and self.engine.tr_geo is not None and self.text_featurizer is not None
+
+    def translate_ids(self, phone_ids: List[int], enc: np.ndarray, pad: int = 10) -> List[int]:
+        """Greedy phone ids + `pad` zeros and the encoder states through the translator -> per-position character argmax
+        (Inference/PythonInference/asr/src/asr.py:77-84)."""
+        seq = np.asarray([list(phone_ids) + [0] * pad], dtype=np.int32)
+        logits = self.engine.translate(seq, np.asarray(enc, dtype=np.float32))
+        return logits[0].argmax(-1).cpu().tolist()
+
     def decode(self, enc_features: List[np.ndarray]) -> str:
-        """List of [1, T_i, D] encoder states (hstacked along time) -> phone string (asr.py:63-94 minus the translator)."""
-        return " ".join(self.phone_featurizer.iextract(self.decode_ids(enc_features)))
+        """List of [1, T_i, D] encoder states (hstacked along time) -> text (asr.py:62-94): CTC greedy phone ids, ten zeros appended,
+        translator, argmax; ids 0 and </S> are dropped and </S> ends the sentence; characters joined without separator.  Without
+        translator weights / tar_config the phone string is returned instead (space separated)."""
+        ids = self.decode_ids(enc_features)
+        if not self.has_translator():
+            return " ".join(self.phone_featurizer.iextract(ids))
+        enc = np.hstack(enc_features) if len(enc_features) > 1 else enc_features[0]
+        end = self.text_featurizer.endid()
+        txt = []
+        for n in self.translate_ids(ids, enc):
+            if n != 0 and n != end:
+                txt.append(n)
+            if n == end:
+                break
+        return "".join(self.text_featurizer.iextract(txt))
+
+    def _text_of(self, phone_ids: List[int], enc: np.ndarray) -> str:
+        """test_asr.py:203-218: translator on the decoded ids as they are (no padding); 0 dropped, everything up to and including </S> kept."""
+        if not self.has_translator() or not phone_ids:
+            return ""
+        end = self.text_featurizer.endid()
+        txt = []
+        for n in self.translate_ids(phone_ids, enc, pad=0):
+            if n != 0:
+                txt.append(n)
+            if n == end:
+                break
+        return "".join(self.text_featurizer.iextract(txt))
 
     # ------------------------------------------------------------------ test_asr.py entry points
     def offline_stt(self, wav_path):
         data = self.speech_featurizer.load_wav(wav_path)
-        ids, lens = self.engine.recognize(np.asarray(data, dtype=np.float32)[None]) if self.beam_width <= 1 else (None, None)
-        if ids is not None:
-            result = [i for i in ids[0, :int(lens[0])].cpu().tolist() if i != 0]     # test_asr.py:206-209 drops id 0 too
+        if self.beam_width <= 1 and not self.has_translator():
+            ids, lens = self.engine.recognize(np.asarray(data, dtype=np.float32)[None])      # one fused call: no logits, no encoder read-back
+            raw_ids, enc = ids[0, :int(lens[0])].cpu().tolist(), None
         else:
-            result = [i for i in self.decode_ids([self.extract_feature(data)]) if i != 0]
-        return " ".join(self.phone_featurizer.iextract(result)), ""
+            enc = self.extract_feature(data)
+            raw_ids = self.decode_ids([enc])
+        result = [i for i in raw_ids if i != 0]                                              # test_asr.py:206-209 drops id 0 too
+        text = self._text_of(raw_ids, enc) if enc is not None else ""
+        return " ".join(self.phone_featurizer.iextract(result)), text
 
     def stream_stt(self, wav_path):
         """test_asr.py:116-165: encode chunk by chunk (each chunk alone), re-decode everything seen so far."""
         data = self.speech_featurizer.load_wav(wav_path)
-        enc_outputs, result = None, []
+        enc_outputs, result, raw_ids = None, [], []
         for s in range(0, len(data), self.chunk):
             enc = self.extract_feature(data[s:s + self.chunk])
             enc_outputs = enc if enc_outputs is None else np.hstack((enc_outputs, enc))
-            result = [i for i in self.decode_ids([enc_outputs]) if i != 0]
-        return " ".join(self.phone_featurizer.iextract(result)), ""
+            raw_ids = self.decode_ids([enc_outputs])
+            result = [i for i in raw_ids if i != 0]
+        text = self._text_of(raw_ids, enc_outputs) if enc_outputs is not None else ""
+        return " ".join(self.phone_featurizer.iextract(result)), text
 
     def stt(self, wav_path):
         return self.stream_stt(wav_path) if self.speech_config["streaming"] else self.offline_stt(wav_path)

@@ -8,21 +8,24 @@ namespace b200asr {
 namespace {
 
 // one warp per row, D <= 512
+// pe (nullable): a [U, D] table added to the row before normalising, row m uses pe row m % U (RMHSAModule: LN(x + positional
+// encoding), conformer_blocks.py:455-456).  round_tf32: the output only feeds a tensor-core GEMM.
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, int M, int D,
-                                                        float eps) {
+                                                        float eps, const float* __restrict__ pe, int U, int round_tf32) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* xr = x + (size_t)row * D;
+  const float* per = pe ? pe + (size_t)(row % U) * D : nullptr;
   float v[16];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int d = lane + i * 32;
-    v[i] = (d < D) ? xr[d] : 0.f;
+    v[i] = (d < D) ? xr[d] + (per ? per[d] : 0.f) : 0.f;
     s += v[i];
   }
   const float mean = warp_sum(s) / (float)D;
@@ -38,8 +41,70 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int d = lane + i * 32;
-    if (d < D) yr[d] = (v[i] - mean) * rstd * gamma[d] + beta[d];
+    if (d < D) {
+      const float o = (v[i] - mean) * rstd * gamma[d] + beta[d];
+      yr[d] = round_tf32 ? tf32_rn(o) : o;
+    }
   }
+}
+
+// x[m, :] = table[clamp(ids[m]), :]   (tf.keras.layers.Embedding)
+__global__ void __launch_bounds__(256) embed_kernel(const int* __restrict__ ids, const float* __restrict__ table, float* __restrict__ x, int M,
+                                                    int D, int n_classes) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (size_t)M * D) return;
+  const int m = (int)(i / D), d = (int)(i - (size_t)m * D);
+  int id = ids[m];
+  id = id < 0 ? 0 : (id >= n_classes ? n_classes - 1 : id);
+  x[i] = table[(size_t)id * D + d];
+}
+
+// Cross attention (RMHSAModule -> MultiHeadAttention([q, enc, enc]), multihead_attention.py:151-188): one warp per (batch, head,
+// query); keys stream 32 at a time with an online softmax.  q [B*U, H*dh] (pre-scaled), kv [B*Tk, 2*H*dh] (k | v), no mask.
+__global__ void __launch_bounds__(128) cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
+                                                              int B, int U, int Tk, int H, int dh, int round_tf32) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 4 + warp;
+  if (gw >= B * H * U) return;
+  const int u = gw % U, h = (gw / U) % H, b = gw / (U * H);
+  const int HD = H * dh;
+  const float* qrow = q + ((size_t)b * U + u) * HD + h * dh;
+  float m_run = -INFINITY, l_run = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int k0 = 0; k0 < Tk; k0 += 32) {
+    const int key = k0 + lane;
+    float sc = -INFINITY;
+    if (key < Tk) {
+      const float* krow = kv + ((size_t)b * Tk + key) * 2 * HD + h * dh;
+      float acc = 0.f;
+      for (int d = 0; d < dh; ++d) acc = fmaf(qrow[d], krow[d], acc);
+      sc = acc;
+    }
+    const float m_new = fmaxf(m_run, warp_max(sc));
+    const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+    const float pj = (key < Tk) ? expf(sc - m_new) : 0.f;
+    l_run = l_run * corr + warp_sum(pj);
+    o0 *= corr;
+    o1 *= corr;
+    const int nk = min(32, Tk - k0);
+    for (int j = 0; j < nk; ++j) {
+      const float pw = __shfl_sync(0xffffffffu, pj, j);
+      const float* vrow = kv + ((size_t)b * Tk + k0 + j) * 2 * HD + HD + h * dh;
+      if (lane < dh) o0 = fmaf(pw, vrow[lane], o0);
+      if (lane + 32 < dh) o1 = fmaf(pw, vrow[lane + 32], o1);
+    }
+    m_run = m_new;
+  }
+  const float inv = 1.0f / l_run;
+  float* orow = out + ((size_t)b * U + u) * HD + h * dh;
+  o0 *= inv;
+  o1 *= inv;
+  if (round_tf32) { o0 = tf32_rn(o0); o1 = tf32_rn(o1); }
+  if (lane < dh) orow[lane] = o0;
+  if (lane + 32 < dh) orow[lane + 32] = o1;
 }
 
 // Flash-style attention on CUDA cores: CTA = (batch, head, 64 queries), 256 threads as 16 x 16; keys/values stream through
@@ -278,14 +343,31 @@ __global__ void __launch_bounds__(256) dwconv_reg2_kernel(const DwConvParams p) 
 }  // namespace
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, float eps,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const float* pe, int U, int round_tf32) {
   if (D > 512) {
     snprintf(g_errbuf, sizeof(g_errbuf), "layernorm: D=%d > 512 unsupported", D);
     return 1;
   }
   if (M == 0) return 0;
-  B200_CUDA_OK(launch_k(layernorm_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, x, gamma, beta, y, M, D, eps));
+  B200_CUDA_OK(launch_k(layernorm_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, x, gamma, beta, y, M, D, eps, pe, U > 0 ? U : 1, round_tf32));
   B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_embed(const int* ids, const float* table, float* x, int M, int D, int n_classes, cudaStream_t stream) {
+  if ((size_t)M * D == 0) return 0;
+  B200_CUDA_OK(launch_k(embed_kernel, dim3((unsigned)(((size_t)M * D + 255) / 256)), dim3(256), 0, stream, ids, table, x, M, D, n_classes));
+  return 0;
+}
+
+int launch_cross_attention(const float* q, const float* kv, float* out, int B, int U, int Tk, int H, int dh, int round_tf32, cudaStream_t stream) {
+  if (dh > 64) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "cross_attention: head_size=%d unsupported (needs <= 64)", dh);
+    return 1;
+  }
+  const int total = B * H * U;
+  if (total == 0 || Tk == 0) return 0;
+  B200_CUDA_OK(launch_k(cross_attention_kernel, dim3(ceil_div(total, 4)), dim3(128), 0, stream, q, kv, out, B, U, Tk, H, dh, round_tf32));
   return 0;
 }
 

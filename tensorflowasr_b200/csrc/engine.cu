@@ -463,6 +463,19 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
                       &h->ctc_blocks[i]))
         return bail(1);
   }
+  if (c.tr_blocks > 0) {
+    h->tr_emb = lookup(h, "tr.emb", (uint64_t)c.tr_inp_classes * D, &ok);
+    h->tr_fcw = ok ? lookup(h, "tr.fc.w", (uint64_t)c.tr_vocab * D, &ok) : nullptr;
+    h->tr_fcb = ok ? lookup(h, "tr.fc.b", c.tr_vocab, &ok) : nullptr;
+    if (!ok) return bail(1);
+    auto it = h->tensors.find("tr.pe");
+    if (it == h->tensors.end() || it->second.second % D != 0) { snprintf(g_errbuf, sizeof(g_errbuf), "b200asr_create: tr.pe (positional table) missing"); return bail(1); }
+    h->tr_pe = it->second.first;
+    h->tr_pe_rows = (int)(it->second.second / D);
+    h->tr_blocks.resize(c.tr_blocks);
+    for (int i = 0; i < c.tr_blocks; ++i)
+      if (!load_block(h, "tr." + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.tr_kernel_size, &h->tr_blocks[i])) return bail(1);
+  }
   if (b200asr::engine_init_frontend(h, weight_blob)) return bail(1);
   {
     ConvSubParams probe{};
@@ -481,6 +494,7 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->chunk) b200asr::chunk_model_free(h->chunk);
   if (h->stage_wav) cudaFree(h->stage_wav);
+  if (h->tr_ws) cudaFree(h->tr_ws);
   if (h->blob_dev) cudaFree(h->blob_dev);
   if (h->twiddle) cudaFree(h->twiddle);
   if (h->mel_lo) cudaFree(h->mel_lo);
@@ -643,6 +657,79 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
   p.workspace = h->beam_ws;
   h->launches += 2;
   ENG_TRY(h, launch_ctc_beam(p, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Translator (conformer_blocks.py:504-552).  The sequences are tiny (U = tokens + 10, two blocks): the schedule is the plain one
+// (LayerNorm kernels + GEMMs through whichever arithmetic the engine runs in), every GEMM on the same kernels as the encoder.
+B200ASR_API int b200asr_translate(b200asr_handle h, const int32_t* ids_dev, const float* enc_dev, int B, int U, int Tp, float* logits_dev,
+                                  void* stream) {
+  if (!h) return 1;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard dev_guard(h->device);
+  if (h->tr_blocks.empty()) return fail(h, "b200asr_translate: the engine was created without a translator (tr_blocks = 0)");
+  if (!ids_dev || !enc_dev || !logits_dev || B < 0 || U < 0 || Tp <= 0) return fail(h, "b200asr_translate: bad arguments");
+  if (B == 0 || U == 0) return 0;
+  if (U > h->tr_pe_rows) return fail(h, "b200asr_translate: sequence longer than the positional table in the blob");
+  const b200asr_config& cfg = h->cfg;
+  const int D = cfg.dmodel, F = cfg.ff_dim, H = cfg.num_heads, dh = cfg.head_size, HD = H * dh, M = B * U, Mk = B * Tp;
+  // workspace: x, xn, att, g [M, D]; hid [M, max(F, 2D)]; q [M, HD]; kv [Mk, 2 HD]
+  const size_t wide = (size_t)std::max(F, 2 * D);
+  const size_t need = (size_t)M * (4 * D + wide + HD) + (size_t)Mk * 2 * HD + 1024;
+  if (need > h->tr_ws_floats) {
+    ENG_CUDA(h, cudaDeviceSynchronize());
+    if (h->tr_ws) ENG_CUDA(h, cudaFree(h->tr_ws));
+    h->tr_ws = nullptr; h->tr_ws_floats = 0;
+    ENG_CUDA(h, cudaMalloc(&h->tr_ws, need * sizeof(float)));
+    h->tr_ws_floats = need;
+  }
+  auto al = [](size_t v) { return (v + 63) / 64 * 64; };
+  float* x = h->tr_ws;
+  float* xn = x + al((size_t)M * D);
+  float* att = xn + al((size_t)M * D);
+  float* g = att + al((size_t)M * D);
+  float* hid = g + al((size_t)M * D);
+  float* q = hid + al((size_t)M * wide);
+  float* kv = q + al((size_t)M * HD);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ctx c{h, st};
+  const bool tc = cfg.precision == B200ASR_PRECISION_TF32;
+  const float eps = cfg.ln_eps;
+  h->launches++;
+  ENG_TRY(h, launch_embed(ids_dev, h->tr_emb, x, M, D, cfg.tr_inp_classes, st));
+  auto ln = [&](const LNW& w, const float* pe) -> int {
+    h->launches++;
+    return launch_layernorm(x, w.g, w.b, xn, M, D, eps, st, pe, U, tc ? 1 : 0);
+  };
+  auto ffn = [&](const FFNW& f) -> int {
+    if (ln(f.ln, nullptr)) return 1;
+    if (gemm(c, xn, D, f.w1, f.b1, nullptr, 0.f, hid, F, M, F, D, EPI_BIAS_SWISH, true)) return 1;
+    return gemm(c, hid, F, f.w2, f.b2, x, 0.5f, x, D, M, D, F, EPI_RESID);
+  };
+  for (const BlockW& w : h->tr_blocks) {
+    ENG_TRY(h, ffn(w.ffn1));
+    // RMHSAModule: queries from LN(x + positions); keys / values straight from the encoder states; residual on x
+    ENG_TRY(h, ln(w.mhsa.ln, h->tr_pe));
+    ENG_TRY(h, gemm(c, xn, D, w.mhsa.wqkv, nullptr, nullptr, 0.f, q, HD, M, HD, D, EPI_NONE));                          // rows [0, HD) of wqkv = Wq (pre-scaled)
+    ENG_TRY(h, gemm(c, enc_dev, D, w.mhsa.wqkv + (size_t)HD * D, nullptr, nullptr, 0.f, kv, 2 * HD, Mk, 2 * HD, D, EPI_NONE));   // rows [HD, 3 HD) = Wk | Wv
+    h->launches++;
+    ENG_TRY(h, launch_cross_attention(q, kv, att, B, U, Tp, H, dh, tc ? 1 : 0, st));
+    ENG_TRY(h, gemm(c, att, HD, w.mhsa.wo, w.mhsa.bo, x, 1.0f, x, D, M, D, HD, EPI_RESID));
+    // ConvModule ('same' padding)
+    ENG_TRY(h, ln(w.conv.ln, nullptr));
+    ENG_TRY(h, gemm(c, xn, D, w.conv.pw1w, w.conv.pw1b, nullptr, 0.f, g, D, M, 2 * D, D, EPI_GLU));
+    DwConvParams dp{};
+    dp.x = g; dp.w = w.conv.dww; dp.y = att; dp.B = B; dp.T = U; dp.D = D; dp.K = w.kernel_size; dp.pad_left = same_pad(U, w.kernel_size, 1).before;
+    dp.round_tf32 = tc ? 1 : 0;
+    h->launches++;
+    ENG_TRY(h, launch_dwconv(dp, st));
+    ENG_TRY(h, gemm(c, att, D, w.conv.pww, w.conv.pwb, nullptr, 0.f, hid, 2 * D, M, 2 * D, D, EPI_BIAS_SWISH, true));
+    ENG_TRY(h, gemm(c, hid, 2 * D, w.conv.pw2w, w.conv.pw2b, x, 1.0f, x, D, M, D, 2 * D, EPI_RESID));
+    ENG_TRY(h, ffn(w.ffn2));
+    h->launches++;
+    ENG_TRY(h, launch_layernorm(x, w.ln.g, w.ln.b, x, M, D, eps, st));
+  }
+  ENG_TRY(h, gemm(c, x, D, h->tr_fcw, h->tr_fcb, nullptr, 0.f, logits_dev, cfg.tr_vocab, M, cfg.tr_vocab, D, EPI_BIAS));
   return 0;
 }
 

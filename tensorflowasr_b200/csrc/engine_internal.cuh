@@ -100,6 +100,12 @@ struct b200asr_engine {
   } pipe[2];
   cudaStream_t pipe_copy = nullptr, pipe_compute = nullptr;
   // b200asr_debug_encode_taps: when set, run_encoder copies the residual stream after the subsampler and after every block
+  // translator (b200asr_translate)
+  std::vector<BlockW> tr_blocks;
+  const float *tr_emb = nullptr, *tr_fcw = nullptr, *tr_fcb = nullptr, *tr_pe = nullptr;
+  int tr_pe_rows = 0;
+  float* tr_ws = nullptr;
+  size_t tr_ws_floats = 0;
   b200asr::ChunkModel* chunk = nullptr;   // set by b200asr_chunk_create: this handle is a ChunkConformer (state-cache streaming) engine
   float* tap_dst = nullptr;
   int tap_count = 0, tap_max = 0;

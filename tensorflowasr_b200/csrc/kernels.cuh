@@ -74,8 +74,12 @@ struct GemmParams {
 int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------- block_ops.cu
+// pe (nullable): [U, D] table added before normalising (row m uses pe row m % U); round_tf32: output rounded to nearest tf32
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, float eps,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const float* pe = nullptr, int U = 1, int round_tf32 = 0);
+int launch_embed(const int* ids, const float* table, float* x, int M, int D, int n_classes, cudaStream_t stream);
+// q [B*U, H*dh] (pre-scaled), kv [B*Tk, 2*H*dh] (k | v) -> out [B*U, H*dh]; no mask
+int launch_cross_attention(const float* q, const float* kv, float* out, int B, int U, int Tk, int H, int dh, int round_tf32, cudaStream_t stream);
 
 struct AttnParams {
   const float* qkv;   // [B*T, 3*H*dh]: q | k | v, each h-major (q already scaled by 1/sqrt(dh) through Wq)

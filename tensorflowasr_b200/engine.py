@@ -28,7 +28,9 @@ class Config(ctypes.Structure):
                 ("n_mels", ctypes.c_int32), ("n_dft", ctypes.c_int32), ("hop", ctypes.c_int32),
                 ("ln_eps", ctypes.c_float),
                 ("chunk_samples", ctypes.c_int32), ("precision", ctypes.c_int32), ("use_cuda_graph", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 8)]
+                ("tr_blocks", ctypes.c_int32), ("tr_kernel_size", ctypes.c_int32), ("tr_inp_classes", ctypes.c_int32),
+                ("tr_vocab", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 4)]
 
 
 _lib = None
@@ -59,6 +61,7 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_ctc_greedy.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]
     if hasattr(lib, "b200asr_ctc_beam"):
         lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
+    lib.b200asr_translate.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
     lib.b200asr_recognize.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_lengths.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
@@ -90,7 +93,8 @@ class Engine:
 
     def __init__(self, enc_geo: W.ModelGeometry, enc_raw: Dict[str, np.ndarray],
                  ctc_geo: Optional[W.ModelGeometry] = None, ctc_raw: Optional[Dict[str, np.ndarray]] = None,
-                 device: int = 0, precision: int = PRECISION_TF32, chunk_samples: int = 0, use_cuda_graph: bool = True):
+                 device: int = 0, precision: int = PRECISION_TF32, chunk_samples: int = 0, use_cuda_graph: bool = True,
+                 tr_geo: Optional[W.ModelGeometry] = None, tr_raw: Optional[Dict[str, np.ndarray]] = None):
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError("b200asr needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -103,7 +107,13 @@ class Engine:
                 if getattr(ctc_geo, f) != getattr(enc_geo, f):
                     raise ValueError(f"CTC decoder {f}={getattr(ctc_geo, f)} differs from the encoder's {getattr(enc_geo, f)}: "
                                      "b200asr_config has a single block geometry")
-        blob = W.pack_blob(W.device_tensors(enc_geo, enc_raw, ctc_geo, ctc_raw, round_tf32=(int(precision) == PRECISION_TF32)))
+        self.tr_geo = tr_geo
+        if tr_geo is not None:
+            for f in ("dmodel", "num_heads", "head_size", "ff_dim"):
+                if getattr(tr_geo, f) != getattr(enc_geo, f):
+                    raise ValueError(f"translator {f}={getattr(tr_geo, f)} differs from the encoder's {getattr(enc_geo, f)}")
+        blob = W.pack_blob(W.device_tensors(enc_geo, enc_raw, ctc_geo, ctc_raw, round_tf32=(int(precision) == PRECISION_TF32),
+                                            tr_geo=tr_geo, tr_raw=tr_raw))
         cfg = Config()
         cfg.abi_version = self.lib.b200asr_abi_version()
         cfg.dmodel, cfg.num_blocks, cfg.num_heads = enc_geo.dmodel, enc_geo.num_blocks, enc_geo.num_heads
@@ -113,6 +123,9 @@ class Engine:
         cfg.vocab = ctc_geo.vocab if ctc_geo else 0
         cfg.n_mels, cfg.n_dft, cfg.hop, cfg.ln_eps = enc_geo.n_mels, enc_geo.n_dft, enc_geo.hop, enc_geo.ln_eps
         cfg.chunk_samples, cfg.precision, cfg.use_cuda_graph = int(chunk_samples), int(precision), int(bool(use_cuda_graph))
+        if tr_geo is not None:
+            cfg.tr_blocks, cfg.tr_kernel_size = tr_geo.num_blocks, tr_geo.kernel_size
+            cfg.tr_inp_classes, cfg.tr_vocab = int(tr_raw["tr.emb"].shape[0]), tr_geo.vocab
         self.cfg = cfg
         h = ctypes.c_void_p()
         torch.cuda.set_device(device)
@@ -236,6 +249,22 @@ class Engine:
                                               float(cutoff_prob), ids.data_ptr(), lens.data_ptr(), scores.data_ptr(),
                                               self._stream()), "b200asr_ctc_beam")
         return ids, lens, scores
+
+    def translate(self, ids, enc):
+        """Translator: ids [B, U] int32 (greedy phone ids, zero padded), enc [B, T', D] -> character logits [B, U, tr_vocab]."""
+        torch = _torch()
+        if self.tr_geo is None:
+            raise RuntimeError("this engine was built without translator weights")
+        ids = torch.as_tensor(np.asarray(ids) if not hasattr(ids, "device") else ids).to(device=self._dev(), dtype=torch.int32).contiguous()
+        if isinstance(enc, np.ndarray):
+            enc = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32))
+        enc = enc.to(device=self._dev(), dtype=torch.float32).contiguous()
+        B, U = ids.shape
+        Tp = enc.shape[1]
+        out = torch.empty((B, U, self.tr_geo.vocab), device=self._dev(), dtype=torch.float32)
+        self._check(self.lib.b200asr_translate(self._h, ids.data_ptr(), enc.data_ptr(), B, U, Tp, out.data_ptr(), self._stream()),
+                    "b200asr_translate")
+        return out
 
     def recognize(self, wav, ids=None, lens=None, frame_lengths=None):
         """wav [B, L] on the GPU -> greedy ids [B, T'] (-1 padded) + lengths, all on the GPU (no sync).  frame_lengths [B]
@@ -391,9 +420,12 @@ class Engine:
 
 def engine_from_onnx(model_dir: str, device: int = 0, precision: int = PRECISION_TF32, chunk_samples: int = 0,
                      use_cuda_graph: bool = True) -> Engine:
-    """Build an Engine from the reference's deployment directory (encoder.onnx + ctc_model.onnx), the same files
-    Inference/PythonInference/asr/src/asr.py:22-25 loads."""
+    """Build an Engine from the reference's deployment directory (encoder.onnx + ctc_model.onnx + translator.onnx when present), the
+    same files Inference/PythonInference/asr/src/asr.py:22-25 loads."""
     ge, re_ = W.import_encoder(os.path.join(model_dir, "encoder.onnx"))
     gc, rc = W.import_ctc_model(os.path.join(model_dir, "ctc_model.onnx"))
+    gt = rt = None
+    if os.path.isfile(os.path.join(model_dir, "translator.onnx")):
+        gt, rt = W.import_translator(os.path.join(model_dir, "translator.onnx"))
     return Engine(ge, re_, gc, rc, device=device, precision=precision, chunk_samples=chunk_samples,
-                  use_cuda_graph=use_cuda_graph)
+                  use_cuda_graph=use_cuda_graph, tr_geo=gt, tr_raw=rt)

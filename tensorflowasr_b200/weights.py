@@ -419,6 +419,37 @@ def import_ctc_model(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
     return geo, raw
 
 
+def import_translator(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
+    """translator.onnx -> (geometry, raw weights).  Graph = Embedding -> N x RBlock(x, enc) -> Dense(tar_classes)
+    (conformer_blocks.py:504-552; an RBlock is a ConformerBlock whose attention takes its keys / values from the encoder states)."""
+    g = load_graph(path)
+    w = _Walker(g)
+    raw: Dict[str, np.ndarray] = {}
+    raw["tr.emb"] = _one(g, r"^embedding/embedding_lookup/\d+:0$")
+    raw["tr.fc.w"] = _one(g, r"^fully_connected/Tensordot/ReadVariableOp:0$")
+    raw["tr.fc.b"] = _one(g, r"^fully_connected/BiasAdd/ReadVariableOp:0$")
+    nb = _count_blocks(g, "decoder_conformer_block_")
+    H = dh = K = 0
+    for i in range(nb):
+        H, dh, K = _import_block(w, f"decoder_conformer_block_{i}/", f"tr.{i}.", raw)
+    D = raw["tr.emb"].shape[1]
+    geo = ModelGeometry(dmodel=D, num_blocks=nb, num_heads=H, head_size=dh, kernel_size=K, ff_dim=raw["tr.0.ffn1.w1"].shape[1],
+                        vocab=raw["tr.fc.b"].shape[0])
+    return geo, raw
+
+
+def translator_positional_encoding(max_len: int, size: int) -> np.ndarray:
+    """The sinusoidal table RMHSAModule adds to its queries (asr/models/layers/positional_encoding.py:19-36), evaluated in float32 in
+    the reference's operation order: sin on the even columns, cos on the odd ones, exponent 2 * (index // 2) / size."""
+    pos = np.arange(max_len, dtype=np.float32)[:, None]
+    index = np.arange(size, dtype=np.float32)[None, :]
+    pe = pos * (np.float32(1.0) / np.power(np.float32(10000.0), (2 * (index // 2)) / np.float32(size)))
+    out = np.zeros((max_len, size), dtype=np.float32)
+    out[:, 0::2] = np.sin(pe[:, 0::2])
+    out[:, 1::2] = np.cos(pe[:, 1::2])
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------
 # synthetic weights (ChunkConformer has no shipped weights; also used by unit tests)
 # --------------------------------------------------------------------------------------------------------
@@ -582,8 +613,12 @@ def round_to_tf32(a: np.ndarray) -> np.ndarray:
     return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
+TRANSLATOR_MAX_TOKENS = 512      # rows of the positional table packed into the blob ("tr.pe")
+
+
 def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_geo: Optional[ModelGeometry] = None,
-                   ctc_raw: Optional[Dict[str, np.ndarray]] = None, round_tf32: bool = False) -> Dict[str, np.ndarray]:
+                   ctc_raw: Optional[Dict[str, np.ndarray]] = None, round_tf32: bool = False,
+                   tr_geo: Optional[ModelGeometry] = None, tr_raw: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
     """round_tf32: round every tensor-core GEMM weight to the nearest tf32 (tf32 precision mode only; the exact-fp32 mode
     keeps the reference's fp32 weights bit for bit)."""
     out: Dict[str, np.ndarray] = {}
@@ -605,10 +640,17 @@ def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_g
             _pack_block(ctc_raw, f"ctc.blk{i}.", f"ctc.blk{i}.", out)
         out["ctc.fc.w"] = ctc_raw["ctc.fc.w"].T                                                 # [V, D]
         out["ctc.fc.b"] = ctc_raw["ctc.fc.b"]
+    if tr_raw is not None:
+        out["tr.emb"] = tr_raw["tr.emb"]
+        for i in range(tr_geo.num_blocks):
+            _pack_block(tr_raw, f"tr.{i}.", f"tr.{i}.", out)
+        out["tr.fc.w"] = tr_raw["tr.fc.w"].T                                                    # [Vt, D]
+        out["tr.fc.b"] = tr_raw["tr.fc.b"]
+        out["tr.pe"] = translator_positional_encoding(TRANSLATOR_MAX_TOKENS, D)
     out = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
     if round_tf32:
         for k in out:
-            if k.endswith(_TC_OPERAND_SUFFIXES) or k in _TC_OPERAND_NAMES:
+            if k.endswith(_TC_OPERAND_SUFFIXES) or k in _TC_OPERAND_NAMES or k == "tr.fc.w":
                 out[k] = round_to_tf32(out[k])
     return out
 

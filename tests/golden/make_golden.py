@@ -33,6 +33,13 @@ out = dict(
     wav_beam_ids=np.asarray([b[1] for b in beam[:4]], dtype=np.int32),
     noise_enc=enc_noise.astype(np.float32), noise_argmax=logits_noise.argmax(-1).astype(np.int32),
 )
+# translator: greedy phone ids + [0] * 10 (Inference/PythonInference/asr/src/asr.py:77) and the encoder states -> character logits
+tpath = os.path.join(md, "translator.onnx")
+if os.path.isfile(tpath):
+    tr_m = ort_ref.OrtModel(tpath, 1)
+    tr_in = np.asarray([out["wav_ids"].tolist() + [0] * 10], dtype=np.int32)
+    tr_out = tr_m.run({"inputs": tr_in, "enc": enc[None].astype(np.float32)})[0]
+    out.update(wav_tr_in=tr_in[0], wav_tr_argmax=tr_out.argmax(-1).astype(np.int32), wav_tr_logits_rows=tr_out[:4].astype(np.float32))
 # streaming models: nine chunks (8 x 8000 + 3263 samples), encoded independently, one CTC decode over all frames
 sd = ort_ref.model_dir("streaming")
 if sd:

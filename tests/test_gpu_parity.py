@@ -438,3 +438,55 @@ def test_config3_full_size_streaming_properties(streaming_weights, ref_wav, torc
         assert lens[r] == int(one_len[0]) and (ids[r, :lens[r]] == one_ids[0, :lens[r]].cpu().numpy()).all()
     assert lens[0] >= 60
     e.close()
+
+
+def test_translator_vs_reference_golden(offline_weights, golden):
+    """b200asr_translate against the reference's translator.onnx on the reference wav: per-position character argmax
+    identical in both precision modes, logits within 2e-3 (fp32 mode) / 5e-2 (tf32)."""
+    import os
+    from oracle import ort_ref, conformer_ref as cr
+    from tensorflowasr_b200 import engine as E, weights as W
+    md = ort_ref.model_dir("offline")
+    if md is None or not os.path.isfile(os.path.join(md, "translator.onnx")):
+        pytest.skip("translator.onnx not staged")
+    ge, re_, gc, rc = offline_weights
+    gt, rt = W.import_translator(os.path.join(md, "translator.onnx"))
+    ref = cr.translator_forward(golden["wav_tr_in"][None], golden["wav_enc"][None], rt, gt.num_blocks)
+    for prec, tol in ((1, 2e-3), (0, 5e-2)):
+        e = E.Engine(ge, re_, gc, rc, precision=prec, tr_geo=gt, tr_raw=rt)
+        out = e.translate(golden["wav_tr_in"][None], golden["wav_enc"][None]).cpu().numpy()
+        assert out.shape == (1, 23, 9160)
+        err = float(np.abs(out - ref).max())
+        print(f"translator precision {prec}: max |logits - oracle| = {err:.3e}")
+        assert (out[0].argmax(-1) == golden["wav_tr_argmax"]).all()
+        np.testing.assert_allclose(out[0, :4], golden["wav_tr_logits_rows"], atol=tol)
+        assert err <= tol
+        two = e.translate(np.stack([golden["wav_tr_in"], golden["wav_tr_in"][::-1].copy()]), np.stack([golden["wav_enc"]] * 2)).cpu().numpy()
+        np.testing.assert_allclose(two[0], out[0], atol=1e-4 if prec else 2e-2)            # batch rows are independent
+        e.close()
+
+
+def test_asr_surface_returns_text(ref_wav):
+    """decode() / stt() return what the reference returns: characters from the translator (asr.py:62-94; test_asr.py:186-218)."""
+    from oracle import ort_ref
+    from tensorflowasr_b200 import asr as A
+    d = ort_ref.model_dir("offline")
+    vocab = os.path.join(ort_ref.REF_DIR, "dict", "pinyin.txt")
+    lm = os.path.join(ort_ref.REF_DIR, "dict", "lm_tokens.txt")
+    if d is None or not all(os.path.isfile(p) for p in (vocab, lm, os.path.join(d, "translator.onnx"))):
+        pytest.skip("translator / vocabularies not staged")
+    cfg = {"running_config": {}, "optimizer_config": {},
+           "speech_config": {"sample_rate": 16000, "frame_ms": 25, "stride_ms": 10, "num_feature_bins": 80, "streaming": False,
+                             "streaming_bucket": 0.5},
+           "model_config": {"dmodel": 144, "num_blocks": 13, "num_heads": 4, "head_size": 36, "kernel_size": 32},
+           "inp_config": {"vocabulary": vocab, "blank_at_zero": False, "beam_width": 1},
+           "tar_config": {"vocabulary": lm, "blank_at_zero": False, "beam_width": 1}}
+    a = A.ASR(cfg)
+    a.compile(d)
+    assert a.has_translator()
+    feat = a.extract_feature(ref_wav)
+    assert a.decode([feat]) == "甚至出现交易几乎停制的情况"
+    wav_path = os.path.join(os.path.dirname(__file__), "golden", "BAC009S0764W0121.wav")
+    phones, text = a.stt(wav_path)
+    assert phones.split(" ") == a.phone_featurizer.iextract(GOLDEN_IDS)
+    assert text.startswith("甚至出现交易几乎停制的情况")

@@ -121,3 +121,24 @@ def test_beam_restatement_vs_reference_cpp(beam, cutoff_prob, cutoff_top_n):
         assert [m[1] for m in mine] == [r[1] for r in ref]
         np.testing.assert_allclose([m[0] for m in mine], [r[0] for r in ref], atol=1e-4)
         assert ctcdec_ref.greedy(probs) == ctc_ref.greedy_decode(probs, V - 1)
+
+
+def test_translator_oracle_pinned_to_reference_golden(golden):
+    """oracle.conformer_ref.translator_forward (embedding -> RBlocks with cross attention over the encoder states -> Dense) against the
+    reference's translator.onnx run by its own onnxruntime on the reference wav (tests/golden/make_golden.py): per-position argmax
+    (= the characters of '甚至出现交易几乎停制的情况' + </S>) identical, logits within 1e-3."""
+    import os
+    from oracle import ort_ref, conformer_ref as cr
+    from tensorflowasr_b200 import weights as W
+    md = ort_ref.model_dir("offline")
+    if md is None or not os.path.isfile(os.path.join(md, "translator.onnx")):
+        pytest.skip("translator.onnx not staged")
+    gt, rt = W.import_translator(os.path.join(md, "translator.onnx"))
+    assert (gt.num_blocks, gt.dmodel, gt.vocab) == (2, 144, 9160)
+    out = cr.translator_forward(golden["wav_tr_in"][None], golden["wav_enc"][None], rt, gt.num_blocks)
+    assert (out[0].argmax(-1) == golden["wav_tr_argmax"]).all()
+    np.testing.assert_allclose(out[0, :4], golden["wav_tr_logits_rows"], atol=1e-3)
+    pe = cr.positional_encoding(7, 6)
+    np.testing.assert_allclose(pe[3], [np.sin(3.0), np.cos(3.0), np.sin(3 / 10000 ** (2 / 6)), np.cos(3 / 10000 ** (2 / 6)),
+                                       np.sin(3 / 10000 ** (4 / 6)), np.cos(3 / 10000 ** (4 / 6))], rtol=1e-5)
+    np.testing.assert_allclose(W.translator_positional_encoding(7, 6), pe, atol=1e-7)
