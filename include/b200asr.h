@@ -107,6 +107,13 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
 B200ASR_API int b200asr_translate(b200asr_handle h, const int32_t* ids_dev /*[B,U]*/, const float* enc_dev /*[B,T',D]*/, int B, int U, int Tp,
                                   float* logits_dev /*[B,U,tr_vocab]*/, void* stream);
 
+/* The same decoder on PROBABILITIES (float32 [B,Tp,V], rows summing to 1) -- the reference decoder's own input convention
+ * (probs_seq, ctc_beam_search_decoder.h:26-45).  With identical probabilities the scores equal the reference C++ decoder's bit for
+ * bit (float log_sum_exp evaluated with correctly rounded exp / log) and so does the hypothesis order. */
+B200ASR_API int b200asr_ctc_beam_probs(b200asr_handle h, const float* probs_dev, const int32_t* lengths_dev, int B, int Tp, int V,
+                           int blank, int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev,
+                           float* scores_dev, void* stream);
+
 /* wav -> greedy token ids in one call, device buffers. */
 B200ASR_API int b200asr_recognize(b200asr_handle h, const float* wav_dev, int B, int L, int32_t* ids_dev /*[B,T']*/,
                       int32_t* out_len_dev /*[B]*/, void* stream);

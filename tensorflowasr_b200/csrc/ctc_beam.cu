@@ -33,23 +33,39 @@ struct FrameTop {   // per frame, produced by beam_prep_kernel
   int n_top;        // entries stored below
 };
 
-__device__ __forceinline__ float class_logprob(float x, float row_max, float row_sum) {
-  const float p = expf(x - row_max) / row_sum;                 // fp32 softmax as the reference callers compute it
-  return (float)log((double)p + (double)FLT_MIN);              // decoder_utils.cpp:33-36
+// is_prob: the input rows already hold probabilities (the reference decoder's own input, probs_seq); else logits, soft-maxed here in fp32
+__device__ __forceinline__ float class_logprob(float x, float row_max, float row_sum, int is_prob) {
+  const float p = is_prob ? x : expf(x - row_max) / row_sum;
+  return (float)log((double)p + (double)FLT_MIN);              // decoder_utils.cpp:33-36: log of a double, stored as float
 }
 
-// float log_sum_exp (decoder_utils.h:42-49)
+// float log_sum_exp (decoder_utils.h:42-49).  The reference instantiates it with T = float: std::exp / std::log are glibc's expf /
+// logf there, which return the correctly rounded float in all but vanishingly rare cases; CUDA's expf / logf do not (2 / 1 ulp).  The
+// same values are produced here by evaluating in double and rounding once, so scores agree with the reference bit for bit and
+// hypotheses can only swap on exact ties -- which prefix_compare resolves the same way (decoder_utils.cpp:137-147).
 __device__ __forceinline__ float lse(float x, float y) {
   if (x <= kNegInf) return y;
   if (y <= kNegInf) return x;
   const float m = fmaxf(x, y);
-  return logf(expf(x - m) + expf(y - m)) + m;
+  const float ex = (float)exp((double)(x - m)), ey = (float)exp((double)(y - m));
+  return (float)log((double)(ex + ey)) + m;
+}
+
+// prefix identity: a hash of the path (root constant, then mixed with every token).  The reference identifies a prefix by its trie
+// node, and a node that was pruned while it still had live children is REVIVED -- same node -- when its parent extends into it again
+// (PathTrie::get_path_trie / remove, path_trie.cpp:37-51,134-152); a path hash gives a re-created prefix its old identity too, so its
+// live children keep recognising it as their parent.
+__device__ __forceinline__ unsigned long long mix_id(unsigned long long parent, int token) {
+  unsigned long long z = parent + 0x9E3779B97F4A7C15ull * (unsigned long long)(token + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
 }
 
 // ---------------------------------------------------------------------------------------------- prep
 __global__ void __launch_bounds__(256) beam_prep_kernel(const float* __restrict__ logits, int rows, int V, int n_store,
                                                         float cutoff_prob, int cutoff_top_n, FrameTop* __restrict__ meta,
-                                                        int* __restrict__ top_idx, float* __restrict__ top_lp) {
+                                                        int* __restrict__ top_idx, float* __restrict__ top_lp, int is_prob) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -58,8 +74,10 @@ __global__ void __launch_bounds__(256) beam_prep_kernel(const float* __restrict_
   for (int v = lane; v < V; v += 32) mx = fmaxf(mx, x[v]);
   mx = warp_max(mx);
   float sm = 0.f;
-  for (int v = lane; v < V; v += 32) sm += expf(x[v] - mx);
-  sm = warp_sum(sm);
+  if (!is_prob) {
+    for (int v = lane; v < V; v += 32) sm += expf(x[v] - mx);
+    sm = warp_sum(sm);
+  }
   // N rounds of "best class strictly after the previous pick" in (value desc, index asc) order
   float pv = INFINITY;
   int pi = -1;
@@ -90,7 +108,7 @@ __global__ void __launch_bounds__(256) beam_prep_kernel(const float* __restrict_
     if (bi == 0x7fffffff) break;
     pv = bv;
     pi = bi;
-    const float p = expf(bv - mx) / sm;
+    const float p = is_prob ? bv : expf(bv - mx) / sm;
     if (lane == 0) {
       top_idx[(size_t)row * n_store + r] = bi;
       top_lp[(size_t)row * n_store + r] = (float)log((double)p + (double)FLT_MIN);
@@ -118,7 +136,8 @@ __global__ void __launch_bounds__(256) beam_prep_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------- search
 struct Entry {
   float b_prev, nb_prev, score, b_cur, nb_cur;
-  int last, id, parent_id, len;
+  int last, len;
+  unsigned long long id, parent_id;
 };
 
 __device__ __forceinline__ unsigned int order_key(float f) {  // larger float -> smaller key (ascending sort = score desc)
@@ -133,7 +152,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
                                                           const float* __restrict__ top_lp, int T, int V, int blank, int beam,
                                                           int n_store, int2* __restrict__ backptr /*[B,T,beam]*/,
                                                           int* __restrict__ ids, int* __restrict__ out_len,
-                                                          float* __restrict__ scores) {
+                                                          float* __restrict__ scores, int is_prob) {
   __shared__ Entry cur[kMaxBeam];
   __shared__ Entry nxt[kMaxBeam];
   __shared__ unsigned long long keys[NSORT];
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
   __shared__ int s_top_idx[kMaxTop];
   __shared__ float s_top_lp[kMaxTop];
   __shared__ int s_child_rank[kMaxBeam + 1];  // ranks (into the top list) of the first beam+1 allowed non-blank classes
-  __shared__ int s_nchild, s_nbeam, s_next_id;
+  __shared__ int s_nchild, s_nbeam;
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const int len = lengths ? min(lengths[b], T) : T;
@@ -149,10 +168,9 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
   if (tid == 0) {
     Entry e;
     e.b_prev = 0.f; e.nb_prev = kNegInf; e.score = 0.f; e.b_cur = kNegInf; e.nb_cur = kNegInf;
-    e.last = -1; e.id = 0; e.parent_id = -1; e.len = 0;
+    e.last = -1; e.id = 0x5851F42D4C957F2Dull; e.parent_id = 0ull; e.len = 0;
     cur[0] = e;
     s_nbeam = 1;
-    s_next_id = 1;
   }
   __syncthreads();
 
@@ -184,10 +202,10 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
           if (s_top_idx[r] == c) return true;
         return false;
       };
-      p.b_cur = allowed(blank) ? class_logprob(x[blank], fm.row_max, fm.row_sum) + p.score : kNegInf;
+      p.b_cur = allowed(blank) ? class_logprob(x[blank], fm.row_max, fm.row_sum, is_prob) + p.score : kNegInf;
       float nb = kNegInf;
       if (p.last >= 0 && allowed(p.last)) {
-        const float lp = class_logprob(x[p.last], fm.row_max, fm.row_sum);
+        const float lp = class_logprob(x[p.last], fm.row_max, fm.row_sum, is_prob);
         nb = lp + p.nb_prev;
         for (int e = 0; e < nbeam; ++e) {
           const Entry& par = cur[e];
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
           e.score = s;
           e.last = c;
           e.parent_id = cur[i].id;
-          e.id = s_next_id + ck;
+          e.id = mix_id(cur[i].id, c);
           e.len = cur[i].len + 1;
           bp = make_int2(i, c);
         }
@@ -303,7 +321,6 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
       int n = 0;
       while (n < beam && keys[n] != ~0ull) ++n;
       s_nbeam = n;
-      s_next_id += ncand_child;
     }
     if (tid < beam) cur[tid] = nxt[tid];
     __syncthreads();
@@ -377,18 +394,18 @@ int launch_ctc_beam(const BeamParams& p, cudaStream_t stream) {
   if (p.T > 0) {
     const int nrows = p.B * p.T;
     beam_prep_kernel<<<ceil_div(nrows, 8), 256, 0, stream>>>(p.logits, nrows, p.V, n_store, p.cutoff_prob, p.cutoff_top_n, meta,
-                                                             top_idx, top_lp);
+                                                             top_idx, top_lp, p.is_prob);
   }
   const int ncand = p.beam + p.beam * (p.beam + 1);
   if (ncand <= 64) {
     beam_search_kernel<64><<<p.B, 256, 0, stream>>>(p.logits, p.lengths, meta, top_idx, top_lp, p.T, p.V, p.blank, p.beam, n_store,
-                                                    backptr, p.ids, p.out_len, p.scores);
+                                                    backptr, p.ids, p.out_len, p.scores, p.is_prob);
   } else if (ncand <= 512) {
     beam_search_kernel<512><<<p.B, 256, 0, stream>>>(p.logits, p.lengths, meta, top_idx, top_lp, p.T, p.V, p.blank, p.beam, n_store,
-                                                     backptr, p.ids, p.out_len, p.scores);
+                                                     backptr, p.ids, p.out_len, p.scores, p.is_prob);
   } else {
     beam_search_kernel<2048><<<p.B, 256, 0, stream>>>(p.logits, p.lengths, meta, top_idx, top_lp, p.T, p.V, p.blank, p.beam,
-                                                      n_store, backptr, p.ids, p.out_len, p.scores);
+                                                      n_store, backptr, p.ids, p.out_len, p.scores, p.is_prob);
   }
   B200_CUDA_OK(cudaGetLastError());
   return 0;

@@ -633,9 +633,23 @@ B200ASR_API int b200asr_ctc_greedy(b200asr_handle h, const float* logits_dev, co
   return 0;
 }
 
+static int ctc_beam_impl(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank, int beam,
+                         int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev, void* stream, int is_prob);
+
 B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank,
                      int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev,
                      void* stream) {
+  return ctc_beam_impl(h, logits_dev, lengths_dev, B, Tp, V, blank, beam, cutoff_top_n, cutoff_prob, ids_dev, out_len_dev, scores_dev, stream, 0);
+}
+
+B200ASR_API int b200asr_ctc_beam_probs(b200asr_handle h, const float* probs_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank,
+                           int beam, int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev,
+                           void* stream) {
+  return ctc_beam_impl(h, probs_dev, lengths_dev, B, Tp, V, blank, beam, cutoff_top_n, cutoff_prob, ids_dev, out_len_dev, scores_dev, stream, 1);
+}
+
+static int ctc_beam_impl(b200asr_handle h, const float* logits_dev, const int32_t* lengths_dev, int B, int Tp, int V, int blank, int beam,
+                         int cutoff_top_n, float cutoff_prob, int32_t* ids_dev, int32_t* out_len_dev, float* scores_dev, void* stream, int is_prob) {
   if (!h) return 1;
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard dev_guard(h->device);
@@ -655,6 +669,7 @@ B200ASR_API int b200asr_ctc_beam(b200asr_handle h, const float* logits_dev, cons
   p.logits = logits_dev; p.lengths = lengths_dev; p.B = B; p.T = Tp; p.V = V; p.blank = blank; p.beam = beam;
   p.cutoff_top_n = cutoff_top_n; p.cutoff_prob = cutoff_prob; p.ids = ids_dev; p.out_len = out_len_dev; p.scores = scores_dev;
   p.workspace = h->beam_ws;
+  p.is_prob = is_prob;
   h->launches += 2;
   ENG_TRY(h, launch_ctc_beam(p, static_cast<cudaStream_t>(stream)));
   return 0;

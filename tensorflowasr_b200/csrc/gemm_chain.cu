@@ -29,6 +29,7 @@ struct ChainParams {
   const float* bias1;   // [N1]
   int n_chunks;         // N1 / CH
   int kb1;              // ceil(K1 / 32) slabs of X
+  int ks1;              // ceil(K1 / 8) k-steps of the first GEMM
   int num_m_tiles;
   long long* dbg;       // optional timeline buffer (B200ASR_CHAIN_DBG=1): [role][event] clock64 stamps of CTA 0
 };
@@ -166,7 +167,8 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const uint64_t da = make_smem_desc(smem_u32(xs + (size_t)kb * kXSlab));
             const uint64_t db = make_smem_desc(smem_u32(ring + (size_t)stage * kRing));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)   // (the last slab of K1 = 144 holds 16 columns: two k-steps, not four)
+            if (kb * 4 + k < p.ks1) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
             tcgen05_commit(&empty_bar[stage]);
             if (kb == p.kb1 - 1) {
               tcgen05_commit(&acc1_full[j & 1]);
@@ -375,6 +377,7 @@ int launch_gemm_chain(TcContext& ctx, const ChainGemmParams& p, int epilogue, cu
   cp.bias1 = p.bias1;
   cp.n_chunks = p.N1 / CH;
   cp.kb1 = ceil_div(p.K1, 32);
+  cp.ks1 = ceil_div(p.K1, 8);
   cp.num_m_tiles = ceil_div(p.M, 128);
   const cuuint32_t ones[2] = {1, 1};
   CUtensorMap mx, m1, m2;

@@ -45,6 +45,7 @@ struct PairParams {
   const float* bias1;
   int nl;            // hidden chunks per CTA
   int kb1;           // ceil(K1 / 32) slabs of X (== kSlabs)
+  int ks1;           // ceil(K1 / 8) k-steps of the first GEMM
   int num_m_tiles;
   long long* dbg;    // optional timeline of cluster 0 / CTA 0 (B200ASR_PAIR_DBG=1): [role][event] clock64 stamps
 };
@@ -183,7 +184,8 @@ gemm_chain_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
           const uint64_t da = make_smem_desc(smem_u32(xs + (size_t)kb * kXSlab));
           const uint64_t db = make_smem_desc(smem_u32(ring + (size_t)stage * kRing));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)   // (the last slab of K1 = 144 holds 16 columns: two k-steps, not four)
+            if (kb * 4 + k < p.ks1) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
           tcgen05_commit(&empty_bar[stage]);
           if (kb == p.kb1 - 1) {
             tcgen05_commit(&acc1_full[jj & 1]);
@@ -447,6 +449,7 @@ int launch_gemm_chain_pair(TcContext& ctx, const ChainGemmParams& p, int epilogu
   const bool direct = (p.N1 == 0);
   pp.nl = direct ? 0 : p.N1 / CH / 2;
   pp.kb1 = ceil_div(p.K1, 32);
+  pp.ks1 = ceil_div(p.K1, 8);
   pp.num_m_tiles = ceil_div(p.M, BM);
   const cuuint32_t ones[2] = {1, 1};
   CUtensorMap mx, m1, m2, mr, mc, mc2;

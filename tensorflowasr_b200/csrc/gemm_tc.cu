@@ -169,10 +169,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = make_smem_desc(sa);
           const uint64_t db = make_smem_desc(sa + kABytes);
+          // k-steps that hold real columns: the last slab of a K = 144 GEMM has 16 (two k-steps), the rest is TMA zero fill
+          const int kcols = (p.a_mode == 0) ? p.K - kb * BLOCK_K : p.D - (kb % p.kc) * BLOCK_K;
+          const int ksteps = kcols >= BLOCK_K ? BLOCK_K / UMMA_K : (kcols + UMMA_K - 1) / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in the 16-byte address field
-            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (k < ksteps) umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[stage]);                           // frees this smem stage when the MMAs retire
           if (kb == p.num_k_blocks - 1) tcgen05_commit(&tmem_full[acc]);  // accumulator complete

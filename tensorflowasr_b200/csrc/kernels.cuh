@@ -122,6 +122,7 @@ struct BeamParams {
   int* out_len;          // [B, beam]
   float* scores;         // [B, beam]
   void* workspace;       // beam_workspace_bytes(B, T, beam)
+  int is_prob = 0;       // 1: `logits` already holds probabilities (the reference decoder's own input convention, probs_seq)
 };
 size_t beam_workspace_bytes(int B, int T, int beam);
 int launch_ctc_beam(const BeamParams& p, cudaStream_t stream);

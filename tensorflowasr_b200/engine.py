@@ -59,8 +59,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_mel.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.b200asr_ctc_logits.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.b200asr_ctc_greedy.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]
-    if hasattr(lib, "b200asr_ctc_beam"):
-        lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
+    lib.b200asr_ctc_beam.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]
+    lib.b200asr_ctc_beam_probs.argtypes = lib.b200asr_ctc_beam.argtypes
     lib.b200asr_translate.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
     lib.b200asr_recognize.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.b200asr_recognize_lengths.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp]
@@ -230,8 +230,9 @@ class Engine:
         return ids, lens
 
     def ctc_beam(self, logits, beam: int, lengths=None, blank: Optional[int] = None, cutoff_top_n: int = 40,
-                 cutoff_prob: float = 1.0):
-        """Prefix beam search (no scorer).  -> (ids [B, beam, T] int32 -1 padded, lens [B, beam], scores [B, beam])."""
+                 cutoff_prob: float = 1.0, probs: bool = False):
+        """Prefix beam search (no scorer).  -> (ids [B, beam, T] int32 -1 padded, lens [B, beam], scores [B, beam]).
+        probs=True: `logits` holds probabilities (the reference decoder's own input); scores then equal the reference's bit for bit."""
         torch = _torch()
         if isinstance(logits, np.ndarray):
             logits = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32))
@@ -245,9 +246,9 @@ class Engine:
         if lengths is not None:
             lengths = torch.as_tensor(lengths, dtype=torch.int32).to(self._dev()).contiguous()
             lptr = lengths.data_ptr()
-        self._check(self.lib.b200asr_ctc_beam(self._h, logits.data_ptr(), lptr, B, T, V, blank, int(beam), int(cutoff_top_n),
-                                              float(cutoff_prob), ids.data_ptr(), lens.data_ptr(), scores.data_ptr(),
-                                              self._stream()), "b200asr_ctc_beam")
+        fn = self.lib.b200asr_ctc_beam_probs if probs else self.lib.b200asr_ctc_beam
+        self._check(fn(self._h, logits.data_ptr(), lptr, B, T, V, blank, int(beam), int(cutoff_top_n), float(cutoff_prob), ids.data_ptr(),
+                       lens.data_ptr(), scores.data_ptr(), self._stream()), "b200asr_ctc_beam")
         return ids, lens, scores
 
     def translate(self, ids, enc):

@@ -490,3 +490,30 @@ def test_asr_surface_returns_text(ref_wav):
     phones, text = a.stt(wav_path)
     assert phones.split(" ") == a.phone_featurizer.iextract(GOLDEN_IDS)
     assert text.startswith("甚至出现交易几乎停制的情况")
+
+
+def test_beam_probability_input_is_bit_exact(eng32):
+    """b200asr_ctc_beam_probs against the reference's own C++ decoder (oracle/_ref/libctcdec_ref.so) on IDENTICAL probabilities: the same
+    hypotheses in the same order and the same float scores, no tie allowance -- small beams on peaky / flat distributions included
+    (the case where a pruned prefix with live children is revived, path_trie.cpp:37-51)."""
+    from oracle import ctc_ref, ctcdec_ref
+    if not ctcdec_ref.available():
+        pytest.skip("oracle/_ref/libctcdec_ref.so not staged")
+    rng = np.random.default_rng(21)
+    cases = [(40, 12, 3.0, 2), (40, 12, 3.0, 3), (60, 8, 1.0, 2), (60, 8, 0.3, 4), (50, 30, 5.0, 4), (80, 1332, 6.0, 16), (125, 1332, 2.0, 16),
+             (30, 6, 0.1, 3), (64, 20, 2.0, 8), (33, 50, 4.0, 32)]
+    n_hyp = 0
+    for (T, V, scale, beam) in cases:
+        logits = (rng.standard_normal((4, T, V)) * scale).astype(np.float32)
+        logits[1, :, V - 1] += 2.0                                             # blank-heavy
+        logits[2, ::3, 2] += 4.0                                               # frequent repeats of one token
+        probs = np.stack([ctc_ref.softmax(l) for l in logits]).astype(np.float32)
+        ids, lens, scores = eng32.ctc_beam(probs, beam, probs=True)
+        ids, lens, scores = ids.cpu().numpy(), lens.cpu().numpy(), scores.cpu().numpy()
+        for b in range(4):
+            ref = ctcdec_ref.beam_search(probs[b].astype(np.float64), beam)
+            got = [ids[b, k, :lens[b, k]].tolist() for k in range(beam) if lens[b, k] >= 0]
+            assert got == [r[1] for r in ref], (T, V, scale, beam, b)
+            np.testing.assert_array_equal(scores[b, :len(ref)], np.asarray([r[0] for r in ref], dtype=np.float32))
+            n_hyp += len(ref)
+    assert n_hyp > 200
