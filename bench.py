@@ -519,7 +519,7 @@ def main():
             tok = torch.full((B_local, geo.dec_back + 4 * T + 1), -1, device="cuda", dtype=torch.int32)
             xch = sharding.IdsExchange(B_local, geo.dec_back + 4 * T, torch.device("cuda", local_rank))
             stats = {"dec_steps": 0, "picked": 0}
-            hchunk = [torch.empty((B_local, S)).pin_memory() for _ in range(2)]
+            hchunks = [host[0][:, k * S:(k + 1) * S].contiguous().pin_memory() for k in range(nsteps_audio)]   # one pinned buffer per 320 ms step
             dchunk = torch.empty((B_local, S), device="cuda")
             hres = torch.empty((world * B_local * (geo.dec_back + 4 * T + 1),), dtype=torch.int32).pin_memory()
 
@@ -548,7 +548,7 @@ def main():
             def e2e_run(n, base):
                 for i in range(n):
                     k = (base + i) % nsteps_audio
-                    dchunk.copy_(host[0][:, k * S:(k + 1) * S], non_blocking=True)      # (a strided pinned slice: one 2-D copy)
+                    dchunk.copy_(hchunks[k], non_blocking=True)
                     sl = one(dchunk)
                     xch.result(sl)
                     hres.copy_(xch.gathered[sl], non_blocking=True)

@@ -129,13 +129,13 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int j = kb / 9, tap = kb - j * 9;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kBBytes);
-          tma_load_2d(&map_b, &full_bar[stage], smem + stage * kStageBytes + kABytes, tap * p.D + j * BLOCK_K, 0);
-          if (++stage == kStg) { stage = 0; phase ^= 1; }
-        }
+        for (int j = 0; j < p.kc; ++j)
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], kBBytes);
+            tma_load_2d(&map_b, &full_bar[stage], smem + stage * kStageBytes + kABytes, tap * p.D + j * BLOCK_K, 0);
+            if (++stage == kStg) { stage = 0; phase ^= 1; }
+          }
       }
     }
   } else if (warp == 1) {
@@ -150,9 +150,9 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int j = kb / 9;
+      for (int j = 0, kb = 0; j < p.kc; ++j) {
         const int ksteps = min(BLOCK_K / UMMA_K, (p.D - j * BLOCK_K + UMMA_K - 1) / UMMA_K);   // the last slab may hold < 32 channels
+        for (int tap = 0; tap < 9; ++tap, ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (lane == 0) {
@@ -165,6 +165,7 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
         }
         __syncwarp();
         if (++stage == kStg) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp < 6) {

@@ -24,7 +24,7 @@ namespace b200asr {
 namespace {
 
 constexpr int kMaxBeam = 32;
-constexpr int kMaxTop = 64;
+constexpr int kMaxTop = 72;   // >= 2 * kMaxBeam + 2 sorted classes per frame (see beam_n_store)
 constexpr float kNegInf = -FLT_MAX;  // NUM_FLT_INF of the reference is FLT_MAX
 
 struct FrameTop {   // per frame, produced by beam_prep_kernel
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
   __shared__ float cand_logp[kMaxBeam * (kMaxBeam + 1)];
   __shared__ int s_top_idx[kMaxTop];
   __shared__ float s_top_lp[kMaxTop];
-  __shared__ int s_child_rank[kMaxBeam + 1];  // ranks (into the top list) of the first beam+1 allowed non-blank classes
-  __shared__ int s_nchild, s_nbeam;
+  __shared__ int cand_cls[kMaxBeam * (kMaxBeam + 1)];   // class of candidate slot i * CW + j (-1 = empty)
+  __shared__ int s_nbeam;
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const int len = lengths ? min(lengths[b], T) : T;
@@ -184,13 +184,6 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
       s_top_lp[tid] = top_lp[row * n_store + tid];
     }
     __syncthreads();
-    if (tid == 0) {
-      int n = 0;
-      const int lim = min(fm.n_top, fm.n_valid);
-      for (int r = 0; r < lim && n < CW; ++r)
-        if (s_top_idx[r] != blank) s_child_rank[n++] = r;
-      s_nchild = n;
-    }
     // 1. survivors: blank and repeated-token transitions (ctc_beam_search_decoder.cpp:88-99), plus -- when the parent of
     //    a live prefix is itself live -- the parent's extension INTO this prefix (:100-131 reaches an existing trie node),
     //    whatever the rank of the token in this frame.
@@ -222,27 +215,52 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
       }
       p.nb_cur = nb;
     }
-    __syncthreads();
-    const int nchild = s_nchild;
-    // 2. extensions that create NEW prefixes (:100-131).  candidate slot = i * CW + j
+    // 2. extensions that create NEW prefixes (:100-131).  candidate slot = i * CW + j.  Per parent, the classes are walked in
+    //    probability order and the first CW that really create a new prefix are taken: blank, classes that lead into a LIVE child of this
+    //    parent (folded into that child above) and a repeat of the parent's last token without blank mass are stepped over -- so a
+    //    parent with k live children still offers its best CW new extensions (the sorted list holds 2 beam + 2 classes for that).
     const int ncand_child = nbeam * CW;
     for (int k = tid; k < ncand_child; k += blockDim.x) {
-      const int i = k / CW, j = k - i * CW;
-      float log_p = kNegInf;
-      if (j < nchild) {
+      cand_logp[k] = kNegInf;
+      cand_cls[k] = -1;
+    }
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int lim = min(fm.n_top, fm.n_valid);
+      for (int i = warp; i < nbeam; i += (int)(blockDim.x >> 5)) {
         const Entry& p = cur[i];
-        const int r = s_child_rank[j];
-        const int c = s_top_idx[r];
-        const float lp = s_top_lp[r];
-        if (c == p.last) {
-          if (p.b_prev > kNegInf) log_p = lp + p.b_prev;
-        } else {
-          log_p = lp + p.score;
+        int taken = 0;
+        for (int r0 = 0; r0 < lim && taken < CW; r0 += 32) {
+          const int r = r0 + lane;
+          bool ok = false;
+          int c = -1;
+          float log_p = kNegInf;
+          if (r < lim) {
+            c = s_top_idx[r];
+            const float lp = s_top_lp[r];
+            ok = (c != blank);
+            if (ok) {
+              if (c == p.last) {
+                if (p.b_prev > kNegInf) log_p = lp + p.b_prev;
+                else ok = false;
+              } else {
+                log_p = lp + p.score;
+              }
+            }
+            if (ok)
+              for (int e = 0; e < nbeam; ++e)
+                if (cur[e].parent_id == p.id && cur[e].last == c) ok = false;     // a live child: already updated in step 1
+          }
+          const unsigned int m = __ballot_sync(0xffffffffu, ok);
+          const int j = taken + __popc(m & ((1u << lane) - 1u));
+          if (ok && j < CW) {
+            cand_logp[i * CW + j] = log_p;
+            cand_cls[i * CW + j] = c;
+          }
+          taken += __popc(m);
         }
-        for (int e = 0; e < nbeam; ++e)
-          if (cur[e].parent_id == p.id && cur[e].last == c) log_p = kNegInf;  // already folded into that live prefix above
       }
-      cand_logp[k] = log_p;
     }
     __syncthreads();
     // 3. keys: survivors first (index < nbeam), then children
@@ -259,8 +277,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
         const int ck = k - nbeam;
         const float s = cand_logp[ck];
         if (s > kNegInf) {
-          const int j = ck % CW;
-          const int c = s_top_idx[s_child_rank[j]];
+          const int c = cand_cls[ck];
           key = ((unsigned long long)order_key(s) << 32) | ((unsigned long long)((c + 1) & 0xffff) << 16) |
                 (unsigned long long)k;
         }
@@ -298,8 +315,8 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const float* __restric
           bp = make_int2(k, -1);
         } else {
           const int ck = k - nbeam;
-          const int i = ck / CW, j = ck - i * CW;
-          const int c = s_top_idx[s_child_rank[j]];
+          const int i = ck / CW;
+          const int c = cand_cls[ck];
           const float s = cand_logp[ck];
           e.b_prev = kNegInf;
           e.nb_prev = s;
@@ -355,8 +372,10 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 }  // namespace
 
+// sorted classes kept per frame: a parent may have up to beam - 1 live children among its best classes, plus the blank, plus a repeat
+// without blank mass, before its `beam` best NEW extensions are reached
 static int beam_n_store(int V, int beam, int cutoff_top_n, float cutoff_prob) {
-  int n = beam + 2;
+  int n = 2 * beam + 2;
   if (cutoff_prob < 1.0f) n = max(n, cutoff_top_n);
   return min(n, V);
 }

@@ -156,22 +156,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
+    const int kdim = (p.a_mode == 0) ? p.K : p.D;                       // columns covered by the slabs of one K run
+    const int tail_cols = kdim - (kdim / BLOCK_K) * BLOCK_K;
+    const int tail_ksteps = tail_cols == 0 ? BLOCK_K / UMMA_K : (tail_cols + UMMA_K - 1) / UMMA_K;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      int slab_j = 0;                        // conv2: channel slab inside the current tap
+      for (int kb = 0; kb < p.num_k_blocks; ++kb, slab_j = (slab_j + 1 == p.kc) ? 0 : slab_j + 1) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = make_smem_desc(sa);
           const uint64_t db = make_smem_desc(sa + kABytes);
-          // k-steps that hold real columns: the last slab of a K = 144 GEMM has 16 (two k-steps), the rest is TMA zero fill
-          const int kcols = (p.a_mode == 0) ? p.K - kb * BLOCK_K : p.D - (kb % p.kc) * BLOCK_K;
-          const int ksteps = kcols >= BLOCK_K ? BLOCK_K / UMMA_K : (kcols + UMMA_K - 1) / UMMA_K;
+          // k-steps that hold real columns: the last slab of a K = 144 GEMM (of every tap of conv2) has 16 columns = two k-steps, the
+          // rest is TMA zero fill.  (No division here: this single thread paces the tensor pipe.)
+          const bool last_slab = (p.a_mode == 0) ? (kb == p.num_k_blocks - 1) : (slab_j == p.kc - 1);
+          const int ksteps = last_slab ? tail_ksteps : BLOCK_K / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in the 16-byte address field
