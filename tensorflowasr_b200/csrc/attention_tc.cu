@@ -111,6 +111,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// cp.async (LDGSTS): the copy engine moves the bytes straight into shared memory, dozens in flight per thread, nothing blocks on the
+// L2 round trip; src_bytes = 0 zero-fills the destination (rows beyond T, padding columns).  Used when the producer of QKV already
+// rounded it to tf32 (the engine's schedule), so that staging does not have to.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B tile made of 32-float slabs of `rows` rows each
 __device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows) {
   const int slab = k >> 5, kk = k & 31;
@@ -216,10 +230,34 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     }
   };
 
+  // asynchronous variants (p.async_stage): same destinations, no rounding (the data is tf32 already)
+  const int nch_real = dh >> 2, nch_total = ((dh + 7) >> 3) << 1;   // 16-byte chunks per row holding data / read by the issued k-steps
+  auto stage_rows_async = [&](uint8_t* dst, const float* src, int row0, int rows, int t0 = 0, int nt = kThreadsA) {
+    const uint32_t d0 = smem_u32a(dst);
+    for (int i = tid - t0; i < rows * (kDP / 4); i += nt) {
+      const int r = i >> 4, c4 = i & 15;
+      if (c4 >= nch_total) continue;
+      const bool real = (row0 + r < p.T) && (c4 < nch_real);
+      cp_async16(d0 + sw128_off(r, 4 * c4, rows), real ? (const void*)(src + (size_t)(row0 + r) * ld + 4 * c4) : (const void*)src, real ? 16 : 0);
+    }
+  };
+  auto stage_vt_async = [&](int k0) {
+    const uint32_t d0 = smem_u32a(Vt);
+    for (int i = tid; i < kKT * dh; i += kThreadsA) {
+      const int key = i & (kKT - 1), d = i >> 8;      // key fastest: conflict-free transposed writes
+      const bool real = (k0 + key < p.T);
+      cp_async4(d0 + sw128_off(d, key, kDP), real ? (const void*)(vbase + (size_t)(k0 + key) * ld + d) : (const void*)vbase, real ? 4 : 0);
+    }
+  };
+  const bool async_stage = p.async_stage != 0;
+
   bool q_staged = false;                          // the next query tile was staged under the previous tile's softmax
   for (int q0 = blockIdx.x * kQT; q0 < p.T; q0 += gridDim.x * kQT) {
   stamp();
-  if (!q_staged) stage_rows(Qs, qbase, q0, kQT);  // rows beyond T and columns beyond dh are zero
+  if (!q_staged) {                                 // rows beyond T and columns beyond dh are zero
+    if (async_stage) stage_rows_async(Qs, qbase, q0, kQT);
+    else stage_rows(Qs, qbase, q0, kQT);
+  }
   q_staged = false;
   stamp();
 
@@ -242,10 +280,16 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
   for (int k0 = 0; k0 < p.T; k0 += kKT) {
     // ---- stage K [256 x 64] and V^T [64 x 256] for this key block
     if (!(single_block && kv_loaded)) {
-      stage_rows(Ks, kbase, k0, kKT);
-      stage_vt(k0);
+      if (async_stage) {
+        stage_rows_async(Ks, kbase, k0, kKT);
+        stage_vt_async(k0);
+      } else {
+        stage_rows(Ks, kbase, k0, kKT);
+        stage_vt(k0);
+      }
       kv_loaded = true;
     }
+    if (async_stage) cp_async_wait_all();          // (also covers the Q tile issued above)
     stamp();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
     fence_before();
@@ -274,7 +318,12 @@ __global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnPa
     const int q_next = q0 + gridDim.x * kQT;
     if (k0 + kKT >= p.T && q_next < p.T) {
       if (warp >= 8) {
-        stage_rows(Qs, qbase, q_next, kQT, 256, kThreadsA - 256);
+        if (async_stage) {
+          stage_rows_async(Qs, qbase, q_next, kQT, 256, kThreadsA - 256);
+          cp_async_wait_all();
+        } else {
+          stage_rows(Qs, qbase, q_next, kQT, 256, kThreadsA - 256);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       q_staged = true;

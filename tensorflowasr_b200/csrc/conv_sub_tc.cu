@@ -222,27 +222,32 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
         }
       }
       asm volatile("bar.sync 3, %0;" ::"n"(kProdThreads) : "memory");
-      // ---- per-pass row geometry (fixed for the tile)
-      int pbase[2], vt[2], vf[2];                 // patch element index of (kh = 0, a = 0, kw = 0, bcol = 0); validity bit masks of kh / kw
-      bool rvalid[2];
+      // ---- per-pass row geometry (fixed for the tile): patch byte address of (kh = 0, a = 0, kw = 0, bc = 0), A-tile byte offsets of the
+      // two 16-byte chunks, and one validity bit per conv2 tap (the row exists, and the conv1 position the tap reads lies inside
+      // conv1's output: outside it conv2 sees its own zero padding, not relu(bias))
+      uint32_t pb8[2], soff0[2], soff1[2];
+      uint32_t okmask[2];
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
         const int r = ps * 64 + rsub;
         const int i = r / p.F2, f2 = r - i * p.F2;
         const int g = tile * p.bt + i;
-        rvalid[ps] = (r < rows_per_tile) && (g < total_trows);
-        const int t2 = rvalid[ps] ? g % p.T2 : 0;
-        pbase[ps] = (rvalid[ps] ? i : 0) * per_row + 4 * f2;
-        int mt = 0, mf = 0;
+        const bool rv = (r < rows_per_tile) && (g < total_trows);
+        const int t2 = rv ? g % p.T2 : 0;
+        pb8[ps] = patch_s + (uint32_t)((rv ? i : 0) * per_row + (rv ? 4 * f2 : 0)) * 8u;
+        soff0[ps] = (uint32_t)r * 128u + (uint32_t)((((2 * cg) ^ (r & 7))) << 4);
+        soff1[ps] = (uint32_t)r * 128u + (uint32_t)((((2 * cg + 1) ^ (r & 7))) << 4);
+        uint32_t m = 0;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int t1 = 2 * t2 + k - p.pt2, f1 = 2 * f2 + k - p.pf2;
-          if (t1 >= 0 && t1 < p.T1) mt |= 1 << k;
-          if (f1 >= 0 && f1 < p.F1) mf |= 1 << k;
-        }
-        vt[ps] = mt;
-        vf[ps] = mf;
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int t1 = 2 * t2 + kh - p.pt2, f1 = 2 * f2 + kw - p.pf2;
+            if (rv && t1 >= 0 && t1 < p.T1 && f1 >= 0 && f1 < p.F1) m |= 1u << (kh * 3 + kw);
+          }
+        okmask[ps] = m;
       }
+      const uint32_t PW8 = (uint32_t)PW * 8u;
       for (int j = 0; j < p.kc; ++j) {
         // conv1 weights of this thread's 8 channels for slab j: w[tap1][4 pairs], bias[4 pairs]
         const int c0 = j * BLOCK_K + 8 * cg;
@@ -254,42 +259,48 @@ conv_subsample_tc_kernel(const __grid_constant__ CUtensorMap map_b, const ConvSu
 #pragma unroll
           for (int t = 0; t < 9; ++t) w[t][q] = cvalid ? lds_u64(w1s_s + (uint32_t)(t * p.D + c0 + 2 * q) * 4u) : 0ull;
         }
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3, kw = tap - kh * 3;
+        // one conv2 tap = one K block.  kh / kw are compile-time constants (no index arithmetic in the body); the nine patch loads of a
+        // pass are issued before the first FMA (they are independent); invalid positions are computed like valid ones and zeroed by a
+        // select, so the body is branch-free.
+        auto do_tap = [&](auto KH, auto KW) {
+          constexpr int kh = decltype(KH)::value, kw = decltype(KW)::value;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t sa = smem_s + (uint32_t)stage * kStageBytes;
 #pragma unroll
           for (int ps = 0; ps < 2; ++ps) {
-            const int r = ps * 64 + rsub;
-            float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-            if (rvalid[ps] && cvalid && ((vt[ps] >> kh) & 1) && ((vf[ps] >> kw) & 1)) {
-              unsigned long long a0 = bias[0], a1 = bias[1], a2 = bias[2], a3 = bias[3];
-              const uint32_t pp = patch_s + (uint32_t)(pbase[ps] + (2 * kh) * PW + 2 * kw) * 8u;
+            const uint32_t pp = pb8[ps] + (uint32_t)(2 * kh) * PW8 + (uint32_t)(2 * kw) * 8u;
+            unsigned long long m[9];
 #pragma unroll
-              for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int bc = 0; bc < 3; ++bc) {
-                  const unsigned long long m = lds_u64(pp + (uint32_t)(a * PW + bc) * 8u);
-                  a0 = cs_ffma2(m, w[a * 3 + bc][0], a0);
-                  a1 = cs_ffma2(m, w[a * 3 + bc][1], a1);
-                  a2 = cs_ffma2(m, w[a * 3 + bc][2], a2);
-                  a3 = cs_ffma2(m, w[a * 3 + bc][3], a3);
-                }
-              }
-              const float2 r0 = relu_rn2(a0), r1 = relu_rn2(a1), r2 = relu_rn2(a2), r3 = relu_rn2(a3);
-              o0 = make_float4(r0.x, r0.y, r1.x, r1.y);
-              o1 = make_float4(r2.x, r2.y, r3.x, r3.y);
+              for (int bc = 0; bc < 3; ++bc) m[a * 3 + bc] = lds_u64(pp + (uint32_t)a * PW8 + (uint32_t)bc * 8u);
+            unsigned long long a0 = bias[0], a1 = bias[1], a2 = bias[2], a3 = bias[3];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              a0 = cs_ffma2(m[t], w[t][0], a0);
+              a1 = cs_ffma2(m[t], w[t][1], a1);
+              a2 = cs_ffma2(m[t], w[t][2], a2);
+              a3 = cs_ffma2(m[t], w[t][3], a3);
             }
+            const bool ok = cvalid && ((okmask[ps] >> (kh * 3 + kw)) & 1u);
+            const float2 r0 = relu_rn2(a0), r1 = relu_rn2(a1), r2 = relu_rn2(a2), r3 = relu_rn2(a3);
+            const float4 o0 = ok ? make_float4(r0.x, r0.y, r1.x, r1.y) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 o1 = ok ? make_float4(r2.x, r2.y, r3.x, r3.y) : make_float4(0.f, 0.f, 0.f, 0.f);
             // K-major SWIZZLE_128B: 16-byte chunk q of row r lives at r * 128 + ((q ^ (r & 7)) << 4)
-            const uint32_t rowp = sa + (uint32_t)r * 128u;
-            sts_v4(rowp + (uint32_t)((((2 * cg) ^ (r & 7))) << 4), o0);
-            sts_v4(rowp + (uint32_t)((((2 * cg + 1) ^ (r & 7))) << 4), o1);
+            sts_v4(sa + soff0[ps], o0);
+            sts_v4(sa + soff1[ps], o1);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[stage]);
           if (++stage == kStg) { stage = 0; phase ^= 1; }
-        }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        do_tap(I0{}, I0{}); do_tap(I0{}, I1{}); do_tap(I0{}, I2{});
+        do_tap(I1{}, I0{}); do_tap(I1{}, I1{}); do_tap(I1{}, I2{});
+        do_tap(I2{}, I0{}); do_tap(I2{}, I1{}); do_tap(I2{}, I2{});
       }
     }
   }

@@ -408,6 +408,7 @@ int engine_init_frontend(b200asr_engine* h, const void* weight_blob) {
   if (const char* e = getenv("B200ASR_NO_CHAIN")) h->use_chain = !(e[0] == '1');
   if (const char* e = getenv("B200ASR_NO_PDL")) g_pdl_enabled = !(e[0] == '1');
   if (const char* e = getenv("B200ASR_NO_PAIR")) h->use_pair = !(e[0] == '1');
+  if (const char* e = getenv("B200ASR_NO_ATTN_ASYNC")) h->attn_async = !(e[0] == '1');
   return 0;
 }
 
@@ -1109,6 +1110,7 @@ B200ASR_API int b200asr_debug_attention(b200asr_handle h, const float* qkv, floa
   DeviceGuard dev_guard(h->device);
   AttnParams ap{};
   ap.qkv = qkv; ap.out = out; ap.B = B; ap.T = T; ap.H = H; ap.dh = dh; ap.win_front = win_front; ap.win_back = win_back;
+  ap.async_stage = (use_tensor_cores == 2) ? 1 : 0;   // 2: the caller's qkv holds tf32 numbers already (cp.async staging, no rounding)
   h->launches++;
   if (use_tensor_cores) {
     if (!attention_tc_supported(ap)) return fail(h, "b200asr_debug_attention: shape not supported by the tcgen05 kernel");

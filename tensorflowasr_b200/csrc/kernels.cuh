@@ -89,6 +89,7 @@ struct AttnParams {
   int win_front, win_back;
   long long* dbg = nullptr;   // optional clock64 timeline of CTA 0 (B200ASR_ATTN_DBG=1)
   int round_tf32 = 0;         // 1: outputs rounded to nearest tf32 (they feed the out-projection's tensor-core A operand only)
+  int async_stage = 0;        // 1 (tcgen05 kernel): qkv holds tf32 numbers already (its producer rounded them): stage Q / K / V^T with cp.async
 };
 int launch_attention(const AttnParams& p, cudaStream_t stream);          // fp32 CUDA cores (block_ops.cu)
 bool attention_tc_supported(const AttnParams& p);

@@ -348,8 +348,9 @@ class Engine:
         """Test hook: qkv [B*T, 3*H*dh] (torch cuda) -> attention output [B*T, H*dh]."""
         torch = _torch()
         out = torch.empty((B * T, H * dh), device=self._dev(), dtype=torch.float32)
+        mode = 2 if tensor_cores == 2 else int(bool(tensor_cores))     # 2: tcgen05 kernel with cp.async staging (qkv already holds tf32 numbers)
         self._check(self.lib.b200asr_debug_attention(self._h, qkv.data_ptr(), out.data_ptr(), B, T, H, dh, int(win_front),
-                                                     int(win_back), int(bool(tensor_cores)), self._stream()), "b200asr_debug_attention")
+                                                     int(win_back), mode, self._stream()), "b200asr_debug_attention")
         return out
 
     def debug_pair_direct(self, X, W, bias, resid, alpha, epilogue, ln1, ln2=None, eps=1e-3):

@@ -114,6 +114,12 @@ def test_attention_kernels_vs_fp64(keng, torch_mod, B, T, H, dh, wf, wb):
     assert not torch.isnan(o_tc).any()
     assert (o_tc.double() - ref).abs().max().item() < 1e-2
     assert (o_32.double() - ref).abs().max().item() < 1e-4
+    # cp.async staging (the engine's schedule: the QKV GEMM stores tf32 numbers, so staging neither rounds nor blocks on loads)
+    qr = ((qkv.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    o_as = keng.debug_attention(qr, B, T, H, dh, 2, wf, wb)
+    o_rn = keng.debug_attention(qr, B, T, H, dh, True, wf, wb)
+    torch.cuda.synchronize()
+    assert torch.equal(o_as, o_rn)              # identical tiles in shared memory -> identical results
 
 
 @pytest.mark.parametrize("M", [8000, 300, 1, 129, 8064])

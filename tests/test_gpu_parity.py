@@ -513,6 +513,15 @@ def test_beam_probability_input_is_bit_exact(eng32):
         for b in range(4):
             ref = ctcdec_ref.beam_search(probs[b].astype(np.float64), beam)
             got = [ids[b, k, :lens[b, k]].tolist() for k in range(beam) if lens[b, k] >= 0]
+            if got != [r[1] for r in ref]:          # diagnostics: where, with which scores, and is it a reordering or a different set
+                refs = [r[1] for r in ref]
+                for k in range(max(len(got), len(refs))):
+                    gk = got[k] if k < len(got) else None
+                    rk = refs[k] if k < len(refs) else None
+                    if gk != rk:
+                        print(f"beam mismatch case {(T, V, scale, beam, b)} at rank {k}: device score {scores[b, k]!r} (this hypothesis is reference rank "
+                              f"{refs.index(gk) if gk in refs else None}), reference score {np.float32(ref[k][0])!r} (reference hypothesis is device rank "
+                              f"{got.index(rk) if rk in got else None}); lengths {len(gk) if gk else None} / {len(rk) if rk else None}")
             assert got == [r[1] for r in ref], (T, V, scale, beam, b)
             np.testing.assert_array_equal(scores[b, :len(ref)], np.asarray([r[0] for r in ref], dtype=np.float32))
             n_hyp += len(ref)

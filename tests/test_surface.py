@@ -97,3 +97,43 @@ def test_sharded_recognize_gloo_world2():
     port = 29500 + os.getpid() % 500
     mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] is True and out[1] is True
+
+
+def _xch_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, T = 3, 5
+    xch = sharding.IdsExchange(B, T, torch.device("cpu"), slots=2)
+    ok = True
+    for step in range(5):                       # more steps than slots: slots are re-acquired after their collective
+        sl = xch.acquire()
+        ids, lens = xch.buffers(sl)
+        ids.fill_(-1)
+        for b in range(B):
+            n = (rank + b + step) % T
+            ids[b, :n] = 100 * rank + 10 * step + b
+            lens[b] = n
+        xch.gather(sl)
+        all_ids, all_lens = xch.result(sl)
+        ok = ok and tuple(all_ids.shape) == (world * B, T) and tuple(all_lens.shape) == (world * B,)
+        for r in range(world):
+            for b in range(B):
+                n = (r + b + step) % T
+                ok = ok and int(all_lens[r * B + b]) == n and bool((all_ids[r * B + b, :n] == 100 * r + 10 * step + b).all()) and \
+                    bool((all_ids[r * B + b, n:] == -1).all())
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ids_exchange_single_collective_gloo_world2():
+    """sharding.IdsExchange: ids and lengths travel in ONE all_gather_into_tensor of a flat buffer the decoder writes in place."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() + 137) % 500
+    mp.spawn(_xch_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] is True and out[1] is True
