@@ -1,4 +1,4 @@
-"""Launch the fused conv1 -> conv2 subsampling kernel alone on the benchmark shape (for ncu)."""
+"""Launch the subsampling convolutions alone on the benchmark shape (for ncu / A-B): B200ASR_FUSED_SUB=1 selects the fused kernel."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

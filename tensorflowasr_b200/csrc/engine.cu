@@ -408,7 +408,7 @@ int engine_init_frontend(b200asr_engine* h, const void* weight_blob) {
   if (const char* e = getenv("B200ASR_NO_CHAIN")) h->use_chain = !(e[0] == '1');
   if (const char* e = getenv("B200ASR_NO_PDL")) g_pdl_enabled = !(e[0] == '1');
   if (const char* e = getenv("B200ASR_NO_PAIR")) h->use_pair = !(e[0] == '1');
-  if (const char* e = getenv("B200ASR_NO_ATTN_ASYNC")) h->attn_async = !(e[0] == '1');
+  if (const char* e = getenv("B200ASR_ATTN_ASYNC")) h->attn_async = (e[0] == '1');
   return 0;
 }
 
@@ -481,8 +481,11 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
   {
     ConvSubParams probe{};
     probe.D = D; probe.F2 = h->F2; probe.B = 1; probe.T = 1; probe.w2 = h->c2w;
-    h->use_fused_sub = c.precision == B200ASR_PRECISION_TF32 && h->tc.ready && conv_subsample_tc_supported(probe);
-    if (const char* e = getenv("B200ASR_NO_FUSED_SUB")) h->use_fused_sub = h->use_fused_sub && !(e[0] == '1');
+    // The fused conv1 -> conv2 kernel removes the conv1 map from HBM (47 MB of DRAM traffic instead of 764 MB per 32 x 10 s batch) but is
+    // SLOWER than the two-kernel path on a B200 (340 us against 262 us: its producer warps recompute conv1 2.25x on CUDA cores and stall
+    // between K blocks, profiles/r02_fused_subsampler.md), and HBM is nowhere near the step's bottleneck: opt-in (B200ASR_FUSED_SUB=1).
+    const char* fe = getenv("B200ASR_FUSED_SUB");
+    h->use_fused_sub = fe && fe[0] == '1' && c.precision == B200ASR_PRECISION_TF32 && h->tc.ready && conv_subsample_tc_supported(probe);
   }
   *out = h;
   return 0;
@@ -966,6 +969,7 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
       case B200ASR_STAGE_ATTENTION: {
         AttnParams ap{};
         ap.qkv = b.h; ap.out = b.att; ap.B = s.B; ap.T = s.T2; ap.H = cfg.num_heads; ap.dh = cfg.head_size; ap.win_front = -1;
+        ap.round_tf32 = 1; ap.async_stage = h->attn_async ? 1 : 0;   // as in run_block_fused (b.h holds the last block's pre-rounded QKV)
         rc = attention(c, ap);
         *flops = 4.0 * s.B * cfg.num_heads * (double)s.T2 * s.T2 * cfg.head_size;
         *bytes = 4.0 * (3.0 * M * cfg.num_heads * cfg.head_size + M * cfg.num_heads * cfg.head_size);

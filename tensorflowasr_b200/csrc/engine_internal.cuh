@@ -84,8 +84,8 @@ struct b200asr_engine {
   std::string err;
   bool use_chain = true;   // chained FFN / conv-tail kernel (B200ASR_NO_CHAIN=1 in the environment turns it off)
   bool use_pair = true;    // ... with the hidden dimension split across a 2-CTA cluster (B200ASR_NO_PAIR=1 turns it off)
-  bool attn_async = true;       // attention stages Q / K / V^T with cp.async from the pre-rounded QKV (B200ASR_NO_ATTN_ASYNC=1 turns it off)
-  bool use_fused_sub = false;   // conv1 computed inside conv2's kernel (tf32 mode; B200ASR_NO_FUSED_SUB=1 turns it off): no conv1 map in HBM
+  bool attn_async = false;      // attention stages Q / K / V^T with cp.async from the pre-rounded QKV (B200ASR_ATTN_ASYNC=1; measured: no gain, 18.2 vs 18.3 us)
+  bool use_fused_sub = false;   // conv1 computed inside conv2's kernel (B200ASR_FUSED_SUB=1; always on in the chunk engine): no conv1 map in HBM
   void* beam_ws = nullptr;
   size_t beam_ws_bytes = 0;
   cudaStream_t own_stream = nullptr;

@@ -197,11 +197,18 @@ def test_subsampling_convs_vs_fp64(torch_mod, B, T):
         return torch.relu(torch.nn.functional.conv2d(x, w.permute(3, 2, 0, 1), b, stride=2))
 
     ref = same_conv(same_conv(mel.double()[:, None], w1, b1), w2, b2).permute(0, 2, 3, 1)     # [B, T2, F2, D]
-    for prec, tol in ((1, 1e-3), (0, 3e-2 * max(1.0, ref.abs().max().item() / 100))):
-        e = E.Engine(ge, re_, gc, rc, precision=prec, use_cuda_graph=False)
+    import os
+    tf32_tol = 3e-2 * max(1.0, ref.abs().max().item() / 100)
+    # exact fp32 kernels; tf32 two-kernel path (conv1 map in HBM + 4-D strided TMA); tf32 fused conv1 -> conv2 kernel (opt-in switch)
+    for prec, fused, tol in ((1, "0", 1e-3), (0, "0", tf32_tol), (0, "1", tf32_tol)):
+        os.environ["B200ASR_FUSED_SUB"] = fused
+        try:
+            e = E.Engine(ge, re_, gc, rc, precision=prec, use_cuda_graph=False)
+        finally:
+            os.environ.pop("B200ASR_FUSED_SUB", None)
         got = e.debug_subsample_convs(mel)
         torch.cuda.synchronize()
         assert tuple(got.shape) == tuple(ref.shape)
         err = (got.double() - ref).abs().max().item()
-        assert err < tol, (prec, err, ref.abs().max().item())
+        assert err < tol, (prec, fused, err, ref.abs().max().item())
         e.close()
