@@ -319,9 +319,14 @@ class Timer:
         # sustained: repeat for >= sustain seconds (chunks of K steps so that the host never runs more than K steps ahead)
         sus = None
         if self.args.sustain > 0:
+            # the number of chunks must be the SAME on every rank (each step issues a collective): derive it from the max-reduced burst time
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            chunks = int(min(max(1.0, -(-self.args.sustain * 1e3 // max(float(t[0]), 1e-3))), 5000))
             n, total_ms = 0, 0.0
-            t0 = time.perf_counter()
-            while time.perf_counter() - t0 < self.args.sustain:
+            for _ in range(chunks):
                 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s0.record()
                 for i in range(self.args.steps):
@@ -595,7 +600,7 @@ def main():
                 tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
                 if os.path.isfile(tpath):
                     traffic = json.load(open(tpath))
-                step(0)
+                eng.recognize(dev[0])            # (no collective here: only rank 0 runs the roofline section) leaves the last block's operands in the workspace
                 torch.cuda.synchronize()
 
                 def stage_line(st, iters=20):

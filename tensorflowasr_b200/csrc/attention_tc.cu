@@ -462,7 +462,11 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
   if (p.B == 0 || p.T == 0) return 0;
   const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + (kKT / 32) * kDP * 128 + 1024 + 64 + 2 * 128 * 2 * 4;   // 96 KB + 3 KB: two CTAs per SM
   static PerDeviceSmem configured;
-  if (configured.need(smem)) B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (configured.need(smem)) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two 99 KB CTAs per SM need the largest shared-memory carve-out
+    B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   // one CTA per (batch, head, query tile): 256 CTAs at the benchmark shape, two resident per SM
   const int qtiles = ceil_div(p.T, kQT);
   dim3 grid(qtiles, p.H, p.B);
