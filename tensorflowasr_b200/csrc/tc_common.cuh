@@ -283,124 +283,6 @@ __device__ __forceinline__ void epilogue_argmax(const TcParams& p, uint32_t tadd
   if (lane < nrows) reinterpret_cast<float2*>(p.C)[(grow0 + lane) * (size_t)p.num_n_tiles + nt] = make_float2(best, __int_as_float(bidx));
 }
 
-// ------------------------------------------------------------------------------------------------ fused LayerNorm epilogues
-// thread == output row and BLOCK_N == N, so a row's statistics never leave the thread: the accumulator row is swept from
-// TMEM two (three) times -- statistics (shifted one-pass variance), then normalise -- instead of being parked in registers.
-template <int EPI, int BLOCK_N>
-__device__ __forceinline__ void epilogue_ln(const TcParams& p, uint32_t taddr, float* wsm, size_t grow0, int nrows, int lane_row,
-                                            int lane) {
-  constexpr bool has_resid = (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2);
-  const bool row_ok = lane_row < nrows;
-  float* Cw = p.C + grow0 * p.ldc;      // this warp's first row in C / C2 / resid
-  float* C2w = p.C2 + grow0 * p.ldc;
-  const float* Rw = has_resid ? p.resid + grow0 * p.ldc : nullptr;
-  // x[c .. c+W) of this thread's row = accumulator + bias (+ residual)
-  auto load_x = [&](auto wtag, int c, float* v) {
-    constexpr int W = decltype(wtag)::value;
-    uint32_t raw[W];
-#pragma unroll
-    for (int j = 0; j < W / 16; ++j) tmem_ld16_nowait(taddr + (uint32_t)(c + 16 * j), raw + 16 * j);   // warp-collective
-    float r[W];
-    if (has_resid) warp_tile_load<W>(wsm, r, Rw + c, p.ldc, nrows, W, lane);
-    tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4 * q));
-      float a0 = __uint_as_float(raw[4 * q + 0]) + b.x, a1 = __uint_as_float(raw[4 * q + 1]) + b.y;
-      float a2 = __uint_as_float(raw[4 * q + 2]) + b.z, a3 = __uint_as_float(raw[4 * q + 3]) + b.w;
-      if (has_resid) {
-        a0 = r[4 * q] + p.alpha * a0; a1 = r[4 * q + 1] + p.alpha * a1; a2 = r[4 * q + 2] + p.alpha * a2; a3 = r[4 * q + 3] + p.alpha * a3;
-      }
-      v[4 * q + 0] = a0; v[4 * q + 1] = a1; v[4 * q + 2] = a2; v[4 * q + 3] = a3;
-    }
-  };
-  auto affine = [&](auto wtag, float* v, float mean, float rstd, const float* g, const float* be, int c) {
-    constexpr int W = decltype(wtag)::value;
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c + 4 * q));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c + 4 * q));
-      v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gg.x + bb.x; v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gg.y + bb.y;
-      v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gg.z + bb.z; v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gg.w + bb.w;
-    }
-  };
-  using W32 = std::integral_constant<int, 32>;
-  using W16 = std::integral_constant<int, 16>;
-  constexpr int FULL = (BLOCK_N / 32) * 32;
-  constexpr bool TAIL = (BLOCK_N % 32) != 0;
-  const float invn = 1.0f / (float)BLOCK_N;
-
-  // sweep 1: x (stored when C keeps the un-normalised stream) + statistics (shifted one-pass variance)
-  float shift = 0.f, s1 = 0.f, s2 = 0.f;
-  auto sweep1 = [&](auto wtag, int c) {
-    constexpr int W = decltype(wtag)::value;
-    float v[W];
-    load_x(wtag, c, v);
-    if (c == 0) shift = v[0];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      const float d = v[i] - shift;
-      s1 += d;
-      s2 = fmaf(d, d, s2);
-    }
-    if (EPI != EPI_RESID_LN2) warp_tile_store<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);
-  };
-#pragma unroll 1
-  for (int c = 0; c < FULL; c += 32) sweep1(W32{}, c);
-  if (TAIL) sweep1(W16{}, FULL);
-  const float m1 = s1 * invn;
-  const float mean1 = shift + m1;
-  const float rstd1 = rsqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
-  if (EPI != EPI_RESID_LN2) {
-    // sweep 2: LN(x; ln1) -> C2   (x read back from C, coalesced: the residual operand may have been overwritten in place)
-    auto sweep2 = [&](auto wtag, int c) {
-      constexpr int W = decltype(wtag)::value;
-      float v[W];
-      warp_tile_load<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);
-      affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
-      warp_tile_store<W>(wsm, v, C2w + c, p.ldc, nrows, W, lane);
-    };
-#pragma unroll 1
-    for (int c = 0; c < FULL; c += 32) sweep2(W32{}, c);
-    if (TAIL) sweep2(W16{}, FULL);
-    return;
-  }
-  // EPI_RESID_LN2: sweep 2: y = LN(x; ln1) -> C, statistics of y; sweep 3: LN(y; ln2) -> C2
-  float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
-  auto sweep2b = [&](auto wtag, int c) {
-    constexpr int W = decltype(wtag)::value;
-    float v[W];
-    load_x(wtag, c, v);
-    affine(wtag, v, mean1, rstd1, p.ln1_g, p.ln1_b, c);
-    if (c == 0) shift2 = v[0];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      const float d = v[i] - shift2;
-      t1 += d;
-      t2 = fmaf(d, d, t2);
-    }
-    warp_tile_store<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);
-  };
-#pragma unroll 1
-  for (int c = 0; c < FULL; c += 32) sweep2b(W32{}, c);
-  if (TAIL) sweep2b(W16{}, FULL);
-  if (p.ln2_g == nullptr) return;
-  const float m2 = t1 * invn;
-  const float mean2 = shift2 + m2;
-  const float rstd2 = rsqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
-  auto sweep3 = [&](auto wtag, int c) {
-    constexpr int W = decltype(wtag)::value;
-    float v[W];
-    warp_tile_load<W>(wsm, v, Cw + c, p.ldc, nrows, W, lane);     // y, as stored in sweep 2
-    affine(wtag, v, mean2, rstd2, p.ln2_g, p.ln2_b, c);
-    warp_tile_store<W>(wsm, v, C2w + c, p.ldc, nrows, W, lane);
-  };
-#pragma unroll 1
-  for (int c = 0; c < FULL; c += 32) sweep3(W32{}, c);
-  if (TAIL) sweep3(W16{}, FULL);
-  (void)row_ok;
-}
-
 // ------------------------------------------------------------------------------------------------ LayerNorm epilogue through a TMA-staged tile
 // The residual tile is fetched by TMA into shared memory while the MMAs run; the epilogue works on it in place (thread ==
 // row, SWIZZLE_128B slabs of 32 columns: conflict-free 16-byte accesses) and the results leave through TMA stores.  No
@@ -560,124 +442,9 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
   };
   const float invn = 1.0f / (float)BLOCK_N;
 
-  // ---- register-resident path (<= 9 units of 16 columns per thread): every TMEM load of the row segment is issued before the
-  // first use, x / y stay in registers between the statistics pass and the normalisation pass (no re-read of TMEM or of the
-  // staging tile), so each value crosses shared memory exactly once per output
-  // MEASURED (B200, round 1): with this path enabled the step went from 1.877 to 1.986 ms and the FFModule kernel from 16.7 to
-  // 17.1 us -- the unrolled body delays the x stores until after the statistics barrier and lengthens the dependent chain in
-  // front of the first TMA store.  Kept for the next iteration on the epilogue, compiled out.
-  constexpr bool kLnRegisterPath = false;
-  constexpr int NU = (HALVES == 2) ? SPLIT : NUNIT;
-  if constexpr (kLnRegisterPath && NU <= 9) {
-    uint32_t xr[NU][16];
-#pragma unroll
-    for (int i = 0; i < NU; ++i)
-      if (u0 + i < u1) tmem_ld16_nowait(taddr + (uint32_t)(16 * (u0 + i)), xr[i]);   // warp-uniform predicate
-    tmem_ld_wait();
-    float shift = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      if (u0 + i < u1) {
-        const int u = u0 + i;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + 16 * u + 4 * q);
-          float a0 = __uint_as_float(xr[i][4 * q + 0]) + b.x, a1 = __uint_as_float(xr[i][4 * q + 1]) + b.y;
-          float a2 = __uint_as_float(xr[i][4 * q + 2]) + b.z, a3 = __uint_as_float(xr[i][4 * q + 3]) + b.w;
-          if (xchg != nullptr) {
-            const float4 o = *chunk_ptr_in(xchg, u, q);
-            a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
-          }
-          if (has_resid) {
-            const float4 r = *chunk_ptr(u, q);
-            a0 = r.x + p.alpha * a0; a1 = r.y + p.alpha * a1; a2 = r.z + p.alpha * a2; a3 = r.w + p.alpha * a3;
-          }
-          xr[i][4 * q + 0] = __float_as_uint(a0); xr[i][4 * q + 1] = __float_as_uint(a1);
-          xr[i][4 * q + 2] = __float_as_uint(a2); xr[i][4 * q + 3] = __float_as_uint(a3);
-        }
-        if (HALVES == 1 && i == 0) shift = __uint_as_float(xr[0][0]);   // shifted one-pass variance when one thread sees the whole row
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float d = __uint_as_float(xr[i][k]) - shift;
-          s1 += d;
-          s2 = fmaf(d, d, s2);
-        }
-      }
-    }
-    combine(s1, s2, 0);
-    const float m1 = s1 * invn;
-    const float mean1 = shift + m1;
-    const float rstd1 = rsqrtf(fmaxf(s2 * invn - m1 * m1, 0.f) + p.ln_eps);
-    // v <- LN(v; g, be) for unit u, in registers
-    auto affine_r = [&](uint32_t* v, float mean, float rstd, const float* g, const float* be, int u) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 gg = *reinterpret_cast<const float4*>(g + 16 * u + 4 * q);
-        const float4 bb = *reinterpret_cast<const float4*>(be + 16 * u + 4 * q);
-        v[4 * q + 0] = __float_as_uint((__uint_as_float(v[4 * q + 0]) - mean) * rstd * gg.x + bb.x);
-        v[4 * q + 1] = __float_as_uint((__uint_as_float(v[4 * q + 1]) - mean) * rstd * gg.y + bb.y);
-        v[4 * q + 2] = __float_as_uint((__uint_as_float(v[4 * q + 2]) - mean) * rstd * gg.z + bb.z);
-        v[4 * q + 3] = __float_as_uint((__uint_as_float(v[4 * q + 3]) - mean) * rstd * gg.w + bb.w);
-      }
-    };
-    auto put_r = [&](uint8_t* base, int u, const uint32_t* v) {
-      if (!active) return;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *chunk_ptr_in(base, u, q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                                __uint_as_float(v[4 * q + 3]));
-    };
-    if (EPI != EPI_RESID_LN2) {
-#pragma unroll
-      for (int i = 0; i < NU; ++i)
-        if (u0 + i < u1) put_r(stile, u0 + i, xr[i]);
-      store_tile(map_c, stile, stile2 == nullptr);         // C = x   (no wait when C2 is staged elsewhere)
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        if (u0 + i < u1) {
-          affine_r(xr[i], mean1, rstd1, p.ln1_g, p.ln1_b, u0 + i);
-          put_r(out2, u0 + i, xr[i]);
-        }
-      }
-      store_tile(map_c2, out2, true);                      // C2 = LN(x; ln1)
-      return;
-    }
-    float shift2 = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      if (u0 + i < u1) {
-        affine_r(xr[i], mean1, rstd1, p.ln1_g, p.ln1_b, u0 + i);
-        if (HALVES == 1 && i == 0) shift2 = __uint_as_float(xr[0][0]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float d = __uint_as_float(xr[i][k]) - shift2;
-          t1 += d;
-          t2 = fmaf(d, d, t2);
-        }
-        put_r(stile, u0 + i, xr[i]);
-      }
-    }
-    if (p.ln2_g == nullptr) {
-      store_tile(map_c, stile, true);
-      return;
-    }
-    store_tile(map_c, stile, stile2 == nullptr);           // C = y = LN(x; ln1)
-    combine(t1, t2, 1);
-    const float m2 = t1 * invn;
-    const float mean2 = shift2 + m2;
-    const float rstd2 = rsqrtf(fmaxf(t2 * invn - m2 * m2, 0.f) + p.ln_eps);
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      if (u0 + i < u1) {
-        affine_r(xr[i], mean2, rstd2, p.ln2_g, p.ln2_b, u0 + i);
-        put_r(out2, u0 + i, xr[i]);
-      }
-    }
-    store_tile(map_c2, out2, true);                        // C2 = LN(y; ln2)
-    return;
-  }
-
-  // ---- generic path (wide rows): the row is swept from TMEM / the staging tile once per pass
+  // (A register-resident variant -- every TMEM load of the row segment issued before the first use, x / y kept in registers between the
+  // statistics and the normalisation pass -- was measured in round 1 and dropped: 1.877 -> 1.986 ms per step, DESIGN.md "tried and dropped".)
+  // the row is swept from TMEM / the staging tile once per pass
   // sweep 1: x (kept in the tile when C holds the un-normalised stream) + statistics
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
