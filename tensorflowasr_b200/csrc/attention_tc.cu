@@ -1,16 +1,17 @@
 // Multi-head self-attention on the 5th-gen tensor cores (tcgen05, tf32 inputs, fp32 accumulate in TMEM).
 //
 // Reference semantics: MultiHeadAttention.call (asr/models/layers/multihead_attention.py:151-188): softmax(Q K^T) V per head,
-// no mask, no positional term, 1/sqrt(d) already folded into Wq.  One CTA = (batch, head, 128 queries), keys in blocks of 128:
-//   * Q [128 x d], K [128 x d] and V^T [d x 128] tiles are written by the CTA's threads straight into the canonical
+// no mask, no positional term, 1/sqrt(d) already folded into Wq.  One CTA = (batch, head, 128 queries):
+//   * Q [128 x d], K [256 x d] and V^T [d x 256] tiles are written by the CTA's threads straight into the canonical
 //     K-major SWIZZLE_128B shared-memory layout (rounded to nearest tf32, zero padded to 64 columns / masked rows), so no
 //     padded copy of the QKV activations is ever needed in HBM;
-//   * S = Q K^T: ceil(d / 8) x tcgen05.mma (M=128, N=128, K=8) into TMEM columns [0,128);
+//   * S = Q K^T: 8 x tcgen05.mma (M=128, N=256, K=8) into TMEM columns [0,256);
 //   * softmax: thread == query row; the row is swept from TMEM twice (max, then exp / sum); P is written back IN PLACE
 //     over S with tcgen05.st (tf32-truncated, and the row sum is taken over the truncated values so the truncation
 //     cancels in the normalisation);
-//   * O_blk = P V: 16 x tcgen05.mma with the A operand read from TMEM (TS form), B = V^T from shared memory, into TMEM
-//     columns [128,192); the running output is kept in registers with the usual online-softmax rescale over the key blocks.
+//   * O_blk = P V: 32 x tcgen05.mma with the A operand read from TMEM (TS form), B = V^T from shared memory, into TMEM
+//     columns [256,320); the running output is kept in registers with the usual online-softmax rescale, so longer
+//     sequences simply loop over 256-key blocks.
 // An optional band (chunk_conformer_blocks.py:158-176) restricts the visible keys per query.
 #include "kernels.cuh"
 
@@ -20,18 +21,12 @@ namespace b200asr {
 
 namespace {
 
-// Round 2 geometry: one CTA = (batch, head, ONE 128-query tile) and keys in blocks of 128, so that a CTA needs 96 KB of shared memory,
-// 192 TMEM columns and 288 threads x <= 112 registers -- TWO CTAs are resident per SM and one's staging / softmax hides under the
-// other's MMAs and TMEM round trips (round 1: one CTA per (batch, head) walking both query tiles with 256-key blocks, 160 KB, 512
-// columns, 384 threads: 128 CTAs on 148 SMs, each a serial latency chain).
 constexpr int kQT = 128;     // queries per CTA
-constexpr int kKT = 128;     // keys per block
-constexpr int kKTLog2 = 7;
+constexpr int kKT = 256;     // keys per block
 constexpr int kDP = 64;      // head dim padded to two 32-float swizzle slabs
-constexpr int kThreadsA = 288;     // warps 0-7: softmax (two per TMEM lane quadrant, 64 key columns each), warp 8: MMA issue + TMEM;
-                                   // all 9 warps: tile staging
+constexpr int kThreadsA = 384;     // warps 0-7: softmax (two per TMEM lane quadrant, 128 key columns each), warp 8: MMA issue +
+                                   // TMEM, all 12 warps: tile staging
 constexpr int kMmaWarp = 8;
-constexpr int kTmemColsA = 256;    // S / P block [0, 128) + O block [128, 192)
 constexpr unsigned kSpin = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,15 +131,15 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows) {
   return (uint32_t)(slab * rows * 128 + row * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2)));
 }
 
-__global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreadsA, 1) attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would strip the address space and turn every
   // access through a derived pointer into a generic LD / ST)
   uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* Qs = smem;                                  // 2 slabs x 128 rows x 128 B = 32 KB
-  uint8_t* Ks = Qs + 2 * kQT * 128;                    // 2 slabs x 128 rows x 128 B = 32 KB
-  uint8_t* Vt = Ks + 2 * kKT * 128;                    // 4 slabs x  64 rows x 128 B = 32 KB   (V transposed: rows = head dim)
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(Vt + (kKT / 32) * kDP * 128);
+  uint8_t* Ks = Qs + 2 * kQT * 128;                    // 2 slabs x 256 rows x 128 B = 64 KB
+  uint8_t* Vt = Ks + 2 * kKT * 128;                    // 8 slabs x  64 rows x 128 B = 64 KB   (V transposed: rows = head dim)
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(Vt + 8 * kDP * 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);      // [2 kinds][128 rows][2 halves] partial max / sum exchange
 
@@ -166,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32a(tmem_slot)), "n"(kTmemColsA) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32a(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_before();
@@ -175,8 +170,8 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
   pdl_trigger();   // TMEM is allocated: the next kernel's CTAs may start their prologue
   pdl_wait();      // QKV (written by the previous kernel) is complete and visible
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;            // columns [0, kKT)
-  const uint32_t tmem_O = tmem_base + kKT;      // columns [kKT, kKT + 64)
+  const uint32_t tmem_S = tmem_base;            // columns [0, 256)
+  const uint32_t tmem_O = tmem_base + kKT;      // columns [256, 320)
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t phase = 0;
   const bool single_block = (p.T <= kKT);       // K / V^T staged once and reused by every query tile of this CTA
@@ -216,7 +211,7 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
 #pragma unroll
       for (int u = 0; u < kSU; ++u) {
         const int i = i0 + u * kThreadsA;
-        const int key = i & (kKT - 1), c4 = i >> kKTLog2;   // key fastest: conflict-free transposed stores
+        const int key = i & (kKT - 1), c4 = i >> 8;   // key fastest: conflict-free transposed stores
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < kKT * (kDP / 4) && k0 + key < p.T && 4 * c4 < dh)
           v[u] = *reinterpret_cast<const float4*>(vbase + (size_t)(k0 + key) * ld + 4 * c4);
@@ -225,7 +220,7 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
       for (int u = 0; u < kSU; ++u) {
         const int i = i0 + u * kThreadsA;
         if (i < kKT * (kDP / 4)) {
-          const int key = i & (kKT - 1), c4 = i >> kKTLog2;
+          const int key = i & (kKT - 1), c4 = i >> 8;
           *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 0, key, kDP)) = to_tf32_rn(v[u].x);
           *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 1, key, kDP)) = to_tf32_rn(v[u].y);
           *reinterpret_cast<float*>(Vt + sw128_off(4 * c4 + 2, key, kDP)) = to_tf32_rn(v[u].z);
@@ -249,7 +244,7 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
   auto stage_vt_async = [&](int k0) {
     const uint32_t d0 = smem_u32a(Vt);
     for (int i = tid; i < kKT * dh; i += kThreadsA) {
-      const int key = i & (kKT - 1), d = i >> kKTLog2;      // key fastest: conflict-free transposed writes
+      const int key = i & (kKT - 1), d = i >> 8;      // key fastest: conflict-free transposed writes
       const bool real = (k0 + key < p.T);
       cp_async4(d0 + sw128_off(d, key, kDP), real ? (const void*)(vbase + (size_t)(k0 + key) * ld + d) : (const void*)vbase, real ? 4 : 0);
     }
@@ -283,7 +278,7 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
   }
 
   for (int k0 = 0; k0 < p.T; k0 += kKT) {
-    // ---- stage K [128 x 64] and V^T [64 x 128] for this key block
+    // ---- stage K [256 x 64] and V^T [64 x 256] for this key block
     if (!(single_block && kv_loaded)) {
       if (async_stage) {
         stage_rows_async(Ks, kbase, k0, kKT);
@@ -448,7 +443,7 @@ __global__ void __launch_bounds__(kThreadsA, 2) attention_tc_kernel(const AttnPa
   __syncthreads();
   if (warp == kMmaWarp) {
     fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsA) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -460,16 +455,12 @@ bool attention_tc_supported(const AttnParams& p) {
 
 int launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
   if (p.B == 0 || p.T == 0) return 0;
-  const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + (kKT / 32) * kDP * 128 + 1024 + 64 + 2 * 128 * 2 * 4;   // 96 KB + 3 KB: two CTAs per SM
+  const size_t smem = (size_t)2 * kQT * 128 + 2 * kKT * 128 + 8 * kDP * 128 + 1024 + 64 + 2 * 128 * 2 * 4;
   static PerDeviceSmem configured;
-  if (configured.need(smem)) {
-    B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two 99 KB CTAs per SM need the largest shared-memory carve-out
-    B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
-  // one CTA per (batch, head, query tile): 256 CTAs at the benchmark shape, two resident per SM
+  if (configured.need(smem)) B200_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // one CTA per (batch, head) when the whole sequence is a single key block (K / V^T staged once for all query tiles)
   const int qtiles = ceil_div(p.T, kQT);
-  dim3 grid(qtiles, p.H, p.B);
+  dim3 grid(p.T <= kKT ? 1 : qtiles, p.H, p.B);
   static long long* dbg = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) {
