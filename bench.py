@@ -279,7 +279,9 @@ def init_dist(local_rank: int, world: int):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a collective that never completes (a rank died, a mismatch) must fail within minutes, not after the 10-minute default
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
         dist.barrier()
         torch.cuda.synchronize()
     finally:

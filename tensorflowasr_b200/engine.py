@@ -232,7 +232,7 @@ class Engine:
     def ctc_beam(self, logits, beam: int, lengths=None, blank: Optional[int] = None, cutoff_top_n: int = 40,
                  cutoff_prob: float = 1.0, probs: bool = False):
         """Prefix beam search (no scorer).  -> (ids [B, beam, T] int32 -1 padded, lens [B, beam], scores [B, beam]).
-        probs=True: `logits` holds probabilities (the reference decoder's own input); scores then equal the reference's bit for bit."""
+        probs=True: `logits` holds probabilities (the reference decoder's own input); scores then equal the reference's to the last bit or two."""
         torch = _torch()
         if isinstance(logits, np.ndarray):
             logits = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32))
