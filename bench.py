@@ -296,6 +296,7 @@ class Timer:
 
     def __init__(self, world: int, args):
         self.world, self.args = world, args
+        self.fork = self.join = lambda: None      # side streams (two batches in flight) wait for / are waited by the timing stream
 
     def barrier(self):
         import torch
@@ -312,8 +313,10 @@ class Timer:
         l0 = launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        self.fork()
         for i in range(self.args.steps):
             step(i)
+        self.join()
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
@@ -331,8 +334,10 @@ class Timer:
             for _ in range(chunks):
                 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s0.record()
+                self.fork()
                 for i in range(self.args.steps):
                     step(n + i)
+                self.join()
                 s1.record()
                 s1.synchronize()
                 total_ms += s0.elapsed_time(s1)
@@ -362,6 +367,8 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained loop (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=1, choices=[1, 2],
+                    help="batches in flight on the device-resident loop (configs 2/3): 2 = two engine handles on two streams, alternate steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -424,6 +431,18 @@ def main():
                        chunk_samples=8000 if kind == "streaming" else 0)
         eng.reserve(B_local, Ls)
         Tp = eng.out_frames(Ls)
+        engs, streams = [eng], [stream]
+        if args.inflight > 1 and kind in ("offline", "streaming"):
+            # a second handle (own workspace + graph cache, same weights) on a second stream: kernels of step i+1 fill the SMs and the
+            # launch gaps step i leaves idle (every kernel of the path is one under-filled wave: 126 CTAs for 148 SMs)
+            for _ in range(args.inflight - 1):
+                e2 = E.Engine(ge, re_, gc, rc, device=local_rank, precision=prec, use_cuda_graph=True,
+                              chunk_samples=8000 if kind == "streaming" else 0)
+                e2.reserve(B_local, Ls)
+                engs.append(e2)
+                streams.append(torch.cuda.Stream())
+            timer.fork = lambda: [s_.wait_stream(stream) for s_ in streams[1:]]
+            timer.join = lambda: [stream.wait_stream(s_) for s_ in streams[1:]]
         # inputs: NROT distinct batches (> L2 together) rotated so that no step re-reads a cached waveform
         host = [torch.from_numpy(synth_batch(cfg["seed"] + 97 * rank + i, cfg["B"] if cfg["scaling"] == "strong" else B_local, Ls,
                                              cfg["speech_every"])[row0:row0 + B_local]).pin_memory() for i in range(NROT)]
@@ -434,28 +453,35 @@ def main():
         # -------------------------------------------------------------------------------------------- step functions
         if kind in ("offline", "streaming"):
             xch = sharding.IdsExchange(B_local, Tp, torch.device("cuda", local_rank))
+            xchs = [xch] + [sharding.IdsExchange(B_local, Tp, torch.device("cuda", local_rank)) for _ in engs[1:]]
+            NI = len(engs)
 
             def step(i):
-                sl = xch.acquire()
-                ids, lens = xch.buffers(sl)
-                eng.recognize(dev[i % NROT], ids, lens)
-                xch.gather(sl)
+                k = i % NI
+                with torch.cuda.stream(streams[k]):
+                    sl = xchs[k].acquire()
+                    ids, lens = xchs[k].buffers(sl)
+                    engs[k].recognize(dev[i % NROT], ids, lens)
+                    xchs[k].gather(sl)
                 return sl
 
             hres = [torch.empty((world * B_local * (Tp + 1),), dtype=torch.int32).pin_memory() for _ in range(2)]
             if world == 1:
-                hid2 = [torch.empty((B_local, Tp), dtype=torch.int32).pin_memory() for _ in range(2)]
-                hlen2 = [torch.empty((B_local,), dtype=torch.int32).pin_memory() for _ in range(2)]
 
-                def e2e_run(n, base):       # two-deep pipeline of the C ABI: H2D of step i+1 under the compute of step i
+                hid2 = [torch.empty((B_local, Tp), dtype=torch.int32).pin_memory() for _ in range(2 * NI)]
+                hlen2 = [torch.empty((B_local,), dtype=torch.int32).pin_memory() for _ in range(2 * NI)]
+
+                def e2e_run(n, base):       # two-deep pipeline of the C ABI per handle: H2D of step i+1 under the compute of step i
+                    D = 2 * NI
                     for i in range(n):
-                        sl = i & 1
-                        if i >= 2:
-                            eng.recognize_host_collect(sl)
-                        eng.recognize_host_submit(sl, host[(base + i) % NROT], hid2[sl], hlen2[sl])
-                    for i in range(max(n - 2, 0), n):
-                        eng.recognize_host_collect(i & 1)
-                e2e_mode = "two-deep pipeline (b200asr_recognize_host_submit/_collect): H2D of step i+1 under the compute of step i"
+                        k, sl = i % NI, (i // NI) & 1
+                        if i >= D:
+                            engs[k].recognize_host_collect(sl)
+                        engs[k].recognize_host_submit(sl, host[(base + i) % NROT], hid2[i % D], hlen2[i % D])
+                    for i in range(max(n - D, 0), n):
+                        engs[i % NI].recognize_host_collect((i // NI) & 1)
+                e2e_mode = ("two-deep pipeline (b200asr_recognize_host_submit/_collect): H2D of step i+1 under the compute of step i"
+                            + (f", alternating over {NI} handles" if NI > 1 else ""))
             else:
                 copy_stream = torch.cuda.Stream()
                 dev_in2 = [torch.empty_like(dev[0]) for _ in range(2)]
@@ -487,7 +513,7 @@ def main():
                         done[i & 1].synchronize()
                 e2e_mode = "two-deep pipeline (copy stream + Engine.recognize + one async all_gather of ids+lengths): H2D of step i+1 under step i"
             h2d_bytes, d2h_bytes = B_local * Ls * 4, world * B_local * (Tp + 1) * 4
-            launch_count = lambda: eng.launch_count
+            launch_count = lambda: sum(e_.launch_count for e_ in engs)
         elif kind == "beam":
             BEAM = 16
             enc = torch.empty((B_local, Tp, ge.dmodel), device="cuda", dtype=torch.float32)
@@ -649,7 +675,7 @@ def main():
                            "seq_len": Ls, "parallelism": f"dp{world} (utterance shard, one async all_gather of ids+lengths per step)",
                            "l2_policy": (f"{NROT} distinct input batches rotated ({NROT * B_local * Ls * 4 / 1e6:.0f} MB > 126 MB L2)" if kind != "chunk" else
                                          "every step reads a new 320 ms chunk per stream; caches + weights (~140 MB) exceed L2"),
-                           "frame": "10 ms hop (160 samples)"},
+                           "frame": "10 ms hop (160 samples)", "batches_in_flight": args.inflight if kind in ("offline", "streaming") else 1},
                 "e2e": {"value": frames_step * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
