@@ -180,6 +180,19 @@ B200ASR_API int b200asr_stream_decoder_step(b200asr_handle h, b200asr_stream st,
 /* rows the next decoder step will produce for n new frames (= carried frames + n) */
 B200ASR_API int b200asr_stream_decoder_rows(b200asr_handle h, b200asr_stream st, int n);
 
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Session layer: the voice-activity model.  Replaces the onnxruntime session of
+ * Inference/PythonInference/vad/src/vad.py:22-28 (`VAD.compile` / `VAD.inference`: vad/models/vad.onnx, input "inputs" f32 [1, N, 80]
+ * = N frames of 80 samples of the 8 kHz signal, output f32 [1, N, 1] logits that the callers threshold at 0:
+ * offline_asr_session.py:79-90, stream_asr_session.py:333-341).
+ *   weight blob  same container as b200asr_create; tensors d0..d3 .w [80, 80] / .b [80] (Dense, [out, in]), c0, c1 .w [80, 5 * 80]
+ *                (causal Conv1D, k = tap * 80 + in) / .b [80], ln.g / ln.b [80], d4.w [4, 80] / d4.b [4] (the single output unit in row 0)
+ *   wav_dev      [B, N * 80 * stride] f32; stride 2 reads every second sample (16 kHz audio in, the callers' `wav[::2]`), stride 1 = 8 kHz
+ *   logits_dev   [B, N] f32.  Exact fp32 (CUDA cores).  The handle is released with b200asr_destroy.
+ */
+B200ASR_API int b200asr_vad_create(const void* weight_blob, size_t blob_bytes, float ln_eps, int device, b200asr_handle* out);
+B200ASR_API int b200asr_vad_infer(b200asr_handle h, const float* wav_dev, int B, int N, int stride, float* logits_dev, void* stream);
+
 /* Roofline instrumentation (bench.py): time one stage of the schedule alone, `iters` launches bracketed by CUDA events on
  * `stream`; also returns that launch's algorithmic FLOPs and HBM bytes.  Run b200asr_recognize with the same (B, L) first. */
 enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 = 2, B200ASR_STAGE_STFT = 3,

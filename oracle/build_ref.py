@@ -50,6 +50,11 @@ def build(verbose: bool = False) -> bool:
             dst = os.path.join(REF, "models", kind, m)
             if not os.path.isfile(dst) and os.path.isfile(os.path.join(MODELS, kind, m)):
                 shutil.copyfile(os.path.join(MODELS, kind, m), dst)
+    # session layer: the voice-activity model (binary, copied as is)
+    os.makedirs(os.path.join(REF, "models", "vad"), exist_ok=True)
+    vad_src = os.path.join(REFERENCE, "Inference/PythonInference/vad/models/vad.onnx")
+    if os.path.isfile(vad_src) and not os.path.isfile(os.path.join(REF, "models", "vad", "vad.onnx")):
+        shutil.copyfile(vad_src, os.path.join(REF, "models", "vad", "vad.onnx"))
     # vocabulary files used by the reference's TextFeaturizer
     os.makedirs(os.path.join(REF, "dict"), exist_ok=True)
     for f in ("pinyin.txt", "lm_tokens.txt"):

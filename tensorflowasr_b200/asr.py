@@ -163,10 +163,14 @@ class ASR:
         self.engine: Optional[E.Engine] = None
 
     # ------------------------------------------------------------------ model loading
-    def compile(self, path: str):
+    def compile(self, path: str, chunked: Optional[bool] = None):
         """`path` holds encoder.onnx + ctc_model.onnx (+ translator.onnx) exactly as the reference's deployment directory does
-        (asr.py:22-25)."""
-        chunk = self.chunk if self.speech_config["streaming"] else 0
+        (asr.py:22-25).  `chunked` (default: speech_config.streaming) makes the engine split every utterance into
+        `streaming_bucket` chunks itself (test_asr.py:116-165); the session layer passes False: it cuts the chunks and hands each one,
+        whatever its length, to extract_feature() as the reference's sessions do."""
+        if chunked is None:
+            chunked = bool(self.speech_config["streaming"])
+        chunk = self.chunk if chunked else 0
         self.engine = E.engine_from_onnx(path, device=self.device, precision=self.precision, chunk_samples=chunk)
         mc = self.model_config or {}
         geo = self.engine.enc_geo

@@ -54,6 +54,8 @@ struct GraphEntry {
 namespace b200asr {
 struct ChunkModel;                                  // chunk_engine.cu: ChunkConformer weights + geometry
 void chunk_model_free(ChunkModel* m);
+struct VadModel;                                    // vad_engine.cu: voice-activity model of the session layer
+void vad_model_free(VadModel* m);
 int engine_alloc(const void* weight_blob, size_t blob_bytes, int device, const char* who, b200asr_engine** out);   // engine.cu
 int engine_init_frontend(b200asr_engine* h, const void* weight_blob);                                            // engine.cu
 }
@@ -108,6 +110,7 @@ struct b200asr_engine {
   float* tr_ws = nullptr;
   size_t tr_ws_floats = 0;
   b200asr::ChunkModel* chunk = nullptr;   // set by b200asr_chunk_create: this handle is a ChunkConformer (state-cache streaming) engine
+  b200asr::VadModel* vad = nullptr;       // set by b200asr_vad_create: this handle is the session layer's voice-activity model
   float* tap_dst = nullptr;
   int tap_count = 0, tap_max = 0;
 };

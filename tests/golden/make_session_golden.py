@@ -5,8 +5,13 @@ asr/src/asr.py, punc_recover/src/punc_recover.py) is imported UNMODIFIED from /r
 substitutions are the three third-party modules this container lacks: `onnxruntime` (-> the reference's own vendored onnxruntime
 1.10.0 binary through oracle/ort_ref.py), `librosa` (-> wave reader, the recording is 16 kHz already) and `soundfile` (unused).
 
-The recording: 0.7 s of faint noise, the reference wav (4.2 s), 1.3 s of faint noise, the first 2.6 s of the wav again, 1.0 s of
-faint noise -- two sentences, so that begin / change / inter-break / end events and the offline segment merge are all exercised.
+Part A (real models).  The recording: faint noise / the reference wav (4.2 s) / noise / the first 2.6 s of the wav, twice over with
+different gaps (about 20 s, four sentences): begin / end events of the streaming session and the > 15 s split of the offline
+segmenter (offline_asr_session.py:184-217) are exercised.
+
+Part B (state machines only).  The reference's ASRSession / TaskContent / OfflineVAD driven by SCRIPTED voice-activity patterns (a
+stub VAD that returns the scripted 0/1 decisions, a stub ASR that returns a description of what it was given): event traces that
+cover the paths real audio rarely reaches (inter-break, result-change accumulation, chunk resets, final_send).
 """
 import json
 import os
@@ -67,8 +72,100 @@ def build_recording():
     x = _read_wav(os.path.join(ROOT, "tests/golden/BAC009S0764W0121.wav"))
     rng = np.random.default_rng(11)
     sil = lambda s: (rng.standard_normal(int(s * 16000)) * 2e-4).astype(np.float32)
-    rec = np.concatenate([sil(0.7), x, sil(1.3), x[:int(2.6 * 16000)], sil(1.0)])
+    rec = np.concatenate([sil(0.7), x, sil(1.3), x[:int(2.6 * 16000)], sil(1.0), x, sil(2.5), x[:int(2.6 * 16000)], sil(1.0)])
+    rec = rec[:len(rec) // 160 * 160]        # (the reference's own reshape at offline_asr_session.py:82 needs a whole number of 160-sample frames)
     return np.clip(np.round(rec * 32768), -32768, 32767).astype("<i2")
+
+
+class ScriptVAD:
+    """Stub for vad/src/vad.py: the k-th call answers with the k-th scripted block of ten 0/1 decisions (as logits +-1) in the LAST ten
+    frames (stream_asr_session.py:341 keeps only those); earlier frames are -1."""
+
+    def __init__(self, script):
+        self.script, self.k = script, 0
+
+    def inference(self, wav):
+        n = wav.shape[1]
+        o = -np.ones((1, n, 1), np.float32)
+        blk = self.script[min(self.k, len(self.script) - 1)]
+        o[0, n - 10:, 0] = np.where(np.asarray(blk) > 0, 1.0, -1.0)
+        self.k += 1
+        return o
+
+
+class ScriptASR:
+    """Stub for asr/src/asr.py: the 'encoder output' of a chunk is its length, the 'text' lists what decode() was handed."""
+
+    def extract_feature(self, wav):
+        return np.asarray([[len(wav)]], np.int64)
+
+    def decode(self, feats):
+        return "decode(" + ",".join(str(int(f[0, 0])) for f in feats) + ")"
+
+
+class ScriptPunc:
+    def punc_recover(self, t):
+        return list(t) + ["<p>"]
+
+
+def make_scripts():
+    """Seeded voice-activity scripts: one block of ten decisions per 100 ms VAD call."""
+    rng = np.random.default_rng(5)
+    scripts = []
+    for n in range(6):
+        blocks, state = [], 0
+        for _ in range(70 + 10 * n):
+            if rng.random() < (0.12 if state else 0.2):
+                state ^= 1
+            p = 0.93 if state else 0.06
+            if rng.random() < 0.25:                        # ragged blocks around the thresholds (5 / 8 of 10)
+                p = rng.choice([0.3, 0.5, 0.7])
+            blocks.append((rng.random(10) < p).astype(np.int32))
+        scripts.append(np.stack(blocks))
+    return scripts
+
+
+def script_pcm(n):
+    """Audio of the scripted runs: its content is irrelevant (the VAD is scripted), only its length matters -- a formula, not stored."""
+    return ((np.arange(n, dtype=np.int64) * 7919) % 6001 - 3000).astype("<i2")
+
+
+def scripted(off, stream):
+    out = {}
+    for si, script in enumerate(make_scripts()):
+        # streaming session: 20 ms packets (320 samples @ 16 kHz), one VAD call per 100 ms
+        ss = stream.ASRSession()
+        ss.asr, ss.punc = ScriptASR(), ScriptPunc()
+        ss.task_content.compile(ScriptVAD(script))
+        pcm = script_pcm(len(script) * 1600)
+        events = []
+        for k, p in enumerate(range(0, len(pcm), 320)):
+            r = ss.send(pcm[p:p + 320].tobytes())
+            if r is not None:
+                events.append({"packet": k, **r})
+        r = ss.final_send()
+        if r is not None:
+            events.append({"packet": -1, **r})
+        out[f"script{si}"] = script.astype(np.int8)
+        out[f"script{si}_events"] = np.frombuffer(json.dumps(events, ensure_ascii=False).encode("utf-8"), dtype=np.uint8)
+        print("script", si, len(events), "events", sorted({e["event_type"] for e in events}))
+        # offline segmenter on the same decisions (one decision per 10 ms frame)
+        ov = off.OfflineVAD(sr=16000)
+
+        class _Whole:
+            def inference(self, wav, s=script):
+                n = wav.shape[1]
+                d = np.concatenate([s.reshape(-1), np.zeros(max(n - s.size, 0), np.int32)])[:n]
+                return np.where(d > 0, 1.0, -1.0).astype(np.float32).reshape(1, n, 1)
+        ov.compile(_Whole())
+        wav = (pcm.astype(np.float32) / 32768)[:len(pcm) // 80 * 80]
+        out[f"script{si}_offline"] = np.asarray(ov.vad(wav), dtype=np.float64).reshape(-1, 2)
+    # the offline merge / split rule on hand-made segment lists (offline_asr_session.py:184-217)
+    ov = off.OfflineVAD(sr=16000)
+    cases = [[[0.5, 3.0], [3.05, 6.0], [6.3, 9.0]], [[0.0, 16.0], [16.05, 31.0]], [[1.0, 47.5], [48.0, 49.0]], [[0.2, 30.2], [31.0, 32.0]],
+             [[0.0, 2.0], [2.05, 14.0], [14.08, 20.0], [20.5, 21.0]]]
+    out["recover_cases"] = np.frombuffer(json.dumps([[c, ov.recover([list(x) for x in c])] for c in cases]).encode(), dtype=np.uint8)
+    return out
 
 
 def main():
@@ -125,6 +222,7 @@ def main():
             events.append({"packet": -1, **r})
         out[tag + "_events"] = np.frombuffer(json.dumps(events, ensure_ascii=False).encode("utf-8"), dtype=np.uint8)
         print(tag, json.dumps(events, ensure_ascii=False, indent=1))
+    out.update(scripted(off, stream))
     np.savez_compressed(os.path.join(ROOT, "tests/golden/session_golden.npz"), **out)
     print("segments", out["offline_segments"].tolist())
     print("responses", json.dumps(responses, ensure_ascii=False))
