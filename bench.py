@@ -367,8 +367,9 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained loop (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=1, choices=[1, 2],
-                    help="batches in flight on the device-resident loop (configs 2/3): 2 = two engine handles on two streams, alternate steps")
+    ap.add_argument("--inflight", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="batches in flight (configs 2/3; sharding.InFlight): n engine handles on n streams, step i on handle i %% n; the single-"
+                         "batch-in-flight time is reported beside it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -431,18 +432,22 @@ def main():
                        chunk_samples=8000 if kind == "streaming" else 0)
         eng.reserve(B_local, Ls)
         Tp = eng.out_frames(Ls)
-        engs, streams = [eng], [stream]
+        pool = None
+        engs = [eng]
         if args.inflight > 1 and kind in ("offline", "streaming"):
-            # a second handle (own workspace + graph cache, same weights) on a second stream: kernels of step i+1 fill the SMs and the
-            # launch gaps step i leaves idle (every kernel of the path is one under-filled wave: 126 CTAs for 148 SMs)
-            for _ in range(args.inflight - 1):
-                e2 = E.Engine(ge, re_, gc, rc, device=local_rank, precision=prec, use_cuda_graph=True,
-                              chunk_samples=8000 if kind == "streaming" else 0)
+            # several batches in flight (sharding.InFlight): one handle per batch in flight (own workspace + graph cache, same weights), each on
+            # its own stream; the kernels of step i+1 fill the SMs and the launch gaps step i leaves idle
+            made = [eng]
+
+            def make_engine():
+                if made:
+                    return made.pop()
+                e2 = E.Engine(ge, re_, gc, rc, device=local_rank, precision=prec, use_cuda_graph=True, chunk_samples=8000 if kind == "streaming" else 0)
                 e2.reserve(B_local, Ls)
-                engs.append(e2)
-                streams.append(torch.cuda.Stream())
-            timer.fork = lambda: [s_.wait_stream(stream) for s_ in streams[1:]]
-            timer.join = lambda: [stream.wait_stream(s_) for s_ in streams[1:]]
+                return e2
+            pool = sharding.InFlight(make_engine, args.inflight, torch.device("cuda", local_rank))
+            engs = pool.engines
+            timer.fork, timer.join = pool.fork, pool.join
         # inputs: NROT distinct batches (> L2 together) rotated so that no step re-reads a cached waveform
         host = [torch.from_numpy(synth_batch(cfg["seed"] + 97 * rank + i, cfg["B"] if cfg["scaling"] == "strong" else B_local, Ls,
                                              cfg["speech_every"])[row0:row0 + B_local]).pin_memory() for i in range(NROT)]
@@ -456,14 +461,22 @@ def main():
             xchs = [xch] + [sharding.IdsExchange(B_local, Tp, torch.device("cuda", local_rank)) for _ in engs[1:]]
             NI = len(engs)
 
-            def step(i):
+            def step1(i):                     # one batch in flight: everything on the timing stream
+                sl = xch.acquire()
+                ids, lens = xch.buffers(sl)
+                eng.recognize(dev[i % NROT], ids, lens)
+                xch.gather(sl)
+                return sl
+
+            def stepn(i):                     # batch i on handle / stream i % NI
                 k = i % NI
-                with torch.cuda.stream(streams[k]):
+                with torch.cuda.stream(pool.stream_of(i)):
                     sl = xchs[k].acquire()
                     ids, lens = xchs[k].buffers(sl)
                     engs[k].recognize(dev[i % NROT], ids, lens)
                     xchs[k].gather(sl)
                 return sl
+            step = stepn if pool is not None else step1
 
             hres = [torch.empty((world * B_local * (Tp + 1),), dtype=torch.int32).pin_memory() for _ in range(2)]
             if world == 1:
@@ -592,12 +605,28 @@ def main():
 
         # -------------------------------------------------------------------------------------------- timing
         warm = max(args.warmup, NROT) if kind != "chunk" else max(args.warmup, 24)    # every rotated input / cache-fill state has its own captured graph
+        if kind in ("offline", "streaming") and pool is not None:
+            import math
+            warm = max(warm, NROT * len(pool) // math.gcd(NROT, len(pool)))          # ... per handle: every (handle, input) pair once
         sampler = ClockSampler(local_rank)
         for i in range(warm):
             step(i)
         timer.barrier()
         sampler.start()
         ms_total, launches, sus = timer.device_timed(step, 0, launch_count)
+        if kind in ("offline", "streaming") and pool is not None:
+            # the same K steps with ONE batch in flight (handle 0 alone, on the timing stream): the per-batch latency view of the step
+            for i in range(NROT):
+                step1(i)
+            timer.barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(args.steps):
+                step1(i)
+            s1.record()
+            timer.barrier()
+            extra["single_batch_in_flight"] = {"ms_per_step": s0.elapsed_time(s1) / args.steps,
+                                               "note": "same loop on one handle / one stream: what one batch costs when nothing else shares the GPU"}
         e2e_run(max(args.warmup, 2), 0)
         timer.barrier()
         t0 = time.perf_counter()
@@ -675,7 +704,7 @@ def main():
                            "seq_len": Ls, "parallelism": f"dp{world} (utterance shard, one async all_gather of ids+lengths per step)",
                            "l2_policy": (f"{NROT} distinct input batches rotated ({NROT * B_local * Ls * 4 / 1e6:.0f} MB > 126 MB L2)" if kind != "chunk" else
                                          "every step reads a new 320 ms chunk per stream; caches + weights (~140 MB) exceed L2"),
-                           "frame": "10 ms hop (160 samples)", "batches_in_flight": args.inflight if kind in ("offline", "streaming") else 1},
+                           "frame": "10 ms hop (160 samples)", "batches_in_flight": (args.inflight if kind in ("offline", "streaming") else 1)},
                 "e2e": {"value": frames_step * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}

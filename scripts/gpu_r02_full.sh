@@ -14,7 +14,7 @@ for c in 3 5 4; do timeout 900 python bench.py --config $c --steps 10 --warmup 3
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sustain 0 > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
   -k "regex:stft_power_warp|db_mel_fast|conv1_f32x2|gemm_tc_kernel|gemm_chain_pair_kernel|attention_tc_kernel|dwconv_reg" \
-  -s 240 -c 14 -o gpurun_out/r02_final python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sustain 0 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+  -s 238 -c 16 -o gpurun_out/r02_final python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sustain 0 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k "regex:gemm_tc_kernel<\(int\)9|argmax_combine|ctc_collapse" -s 3 -c 3 -o gpurun_out/r02_ctcfc python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sustain 0 > gpurun_out/ncu_ctcfc.log 2>&1; echo "ncu ctc head rc=$?"
 python - <<'PY'
 import json

@@ -77,7 +77,10 @@ def main():
     md += ["", "Per-stage DRAM bytes of ONE launch (first occurrence in the capture) -> `profiles/ncu_traffic.json`, read by `bench.py` for",
            "`roofline.traffic` / `other_stages.*.traffic`."]
     open(os.path.join(ROOT, "profiles", "r02_ncu_full_top_kernels.md"), "w").write("\n".join(md) + "\n")
-    json.dump({k: round(v) for k, v in traffic.items()}, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    merged = json.load(open(tpath)) if os.path.isfile(tpath) else {}          # stages this capture does not cover keep their earlier value
+    merged.update({k: round(v) for k, v in traffic.items()})
+    json.dump(merged, open(tpath, "w"), indent=1)
     print("\n".join(md))
     print(traffic)
 

@@ -104,3 +104,54 @@ def recognize_sharded(engine, wavs, group=None):
     b0, b1 = shard_range(len(wavs), rank, world)
     ids, lens = engine.recognize(wavs[b0:b1])
     return gather_ids(ids, lens, group)
+
+
+class InFlight:
+    """Several batches in flight on ONE GPU: `n` engine handles (same weights; own workspace and CUDA-graph cache each) on `n` streams,
+    batch i goes to handle i % n.  Every kernel of the path is a single under-filled wave (126 CTAs of one per SM on 148 SMs at
+    32 x 10 s) with a serial load -> MMA -> epilogue chain inside each CTA, so the kernels of batch i+1 fill the SMs and the launch
+    gaps batch i leaves idle: measured +12.7 % frames/s at two in flight on configs[1] (profiles/r02_bench_c2_two_in_flight.json
+    against ..._single_in_flight.json).  The latency of ONE batch does not improve (it grows slightly); this is a throughput mode.
+
+    `make_engine()` builds one handle.  `fork()` makes the side streams wait for the caller's current stream (inputs written
+    there), `join()` makes the caller's stream wait for all of them; between the two, `stream_of(i)` is the stream batch i runs on."""
+
+    def __init__(self, make_engine, n: int = 2, device=None):
+        import torch
+        if n < 1:
+            raise ValueError("InFlight: n must be >= 1")
+        self.engines = [make_engine() for _ in range(n)]
+        self.device = torch.device("cuda", self.engines[0].device) if device is None else device
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(n)]
+
+    def __len__(self):
+        return len(self.engines)
+
+    def stream_of(self, i: int):
+        return self.streams[i % len(self.streams)]
+
+    def engine_of(self, i: int):
+        return self.engines[i % len(self.engines)]
+
+    def fork(self):
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def join(self):
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def recognize(self, i: int, wav, ids=None, lens=None, frame_lengths=None):
+        """Batch i: Engine.recognize on handle / stream i % n (no host sync).  Returns (ids, lens) on the GPU; they are complete once
+        `stream_of(i)` has reached this point (join(), or an event recorded on that stream)."""
+        import torch
+        with torch.cuda.stream(self.stream_of(i)):
+            return self.engine_of(i).recognize(wav, ids, lens, frame_lengths)
+
+    @property
+    def launch_count(self) -> int:
+        return sum(e.launch_count for e in self.engines)
