@@ -31,6 +31,8 @@ constexpr int kF = 80, kPad = 4, kTaps = 5;
 
 // X[b, 4 + n, c] = wav[b, (n * 80 + c) * stride]; rows 0..3 of every session = 0
 __global__ void vad_pack_kernel(const float* __restrict__ wav, float* __restrict__ X, int B, int N, int stride) {
+  pdl_trigger();
+  pdl_wait();      // (launched with the programmatic-dependent-launch attribute like every kernel here: wait for the producer's writes)
   const size_t total = (size_t)B * (N + kPad) * kF;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % kF);
@@ -42,6 +44,8 @@ __global__ void vad_pack_kernel(const float* __restrict__ wav, float* __restrict
 }
 
 __global__ void vad_zero_pad_kernel(float* __restrict__ X, int B, int N) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kPad * kF) return;
   const int b = i / (kPad * kF), k = i % (kPad * kF);
@@ -50,6 +54,8 @@ __global__ void vad_zero_pad_kernel(float* __restrict__ X, int B, int N) {
 
 // logits[b, n] = Y[(b * (N + 4) + 4 + n) * 4]
 __global__ void vad_unpack_kernel(const float* __restrict__ Y, float* __restrict__ logits, int B, int N) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * N) return;
   const int b = i / N, n = i % N;

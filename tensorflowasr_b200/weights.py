@@ -371,10 +371,37 @@ def _count_blocks(g: Graph, stem: str) -> int:
     return len(idx)
 
 
+def _own_export(g: Graph, kind: str):
+    """Files written by onnx_export.py keep every weight as an initializer under its own key: read them back verbatim."""
+    from .onnx_export import PREFIX
+    raw = {k[len(PREFIX):]: np.asarray(v) for k, v in g.initializers.items() if k.startswith(PREFIX)}
+    if not raw:
+        return None
+    stem = {"encoder": "enc.{}.", "ctc": "ctc.blk{}.", "translator": "tr.{}."}[kind]
+    nb = 0
+    while stem.format(nb) + "ln.g" in raw:
+        nb += 1
+    if nb == 0:
+        raise ValueError(f"exported {kind} graph holds no block weights")
+    b0 = stem.format(0)
+    H, D, dh = raw[b0 + "mhsa.wq"].shape
+    kw = dict(dmodel=D, num_blocks=nb, num_heads=H, head_size=dh, kernel_size=raw[b0 + "conv.dw.w"].shape[0], ff_dim=raw[b0 + "ffn1.w1"].shape[1])
+    if kind == "encoder":
+        kw.update(n_mels=raw["fe.mel"].shape[1], n_dft=raw["fe.window"].shape[0])
+    elif kind == "ctc":
+        kw.update(vocab=raw["ctc.fc.b"].shape[0])
+    else:
+        kw.update(vocab=raw["tr.fc.b"].shape[0])
+    return ModelGeometry(**kw), raw
+
+
 def import_encoder(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
     """encoder.onnx -> (geometry, raw weights).  Graph = Melspectrogram -> ConvSubsampling -> N x ConformerBlock
     (conformer_blocks.py:343-356)."""
     g = load_graph(path)
+    own = _own_export(g, "encoder")
+    if own is not None:
+        return own
     w = _Walker(g)
     raw: Dict[str, np.ndarray] = {}
     real = _one(g, r"^melspectrogram/convolution/ReadVariableOp:0$")              # [513,1,1024,1] cos * hann
@@ -403,6 +430,9 @@ def import_ctc_model(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
     """ctc_model.onnx -> (geometry, raw weights).  Graph = Dense -> N x ConformerBlock -> Dense(V)
     (conformer_blocks.py:419-424)."""
     g = load_graph(path)
+    own = _own_export(g, "ctc")
+    if own is not None:
+        return own
     w = _Walker(g)
     raw: Dict[str, np.ndarray] = {}
     raw["ctc.fc.w"] = _one(g, r"^fully_connected/Tensordot/ReadVariableOp:0$")
@@ -423,6 +453,9 @@ def import_translator(path: str) -> Tuple[ModelGeometry, Dict[str, np.ndarray]]:
     """translator.onnx -> (geometry, raw weights).  Graph = Embedding -> N x RBlock(x, enc) -> Dense(tar_classes)
     (conformer_blocks.py:504-552; an RBlock is a ConformerBlock whose attention takes its keys / values from the encoder states)."""
     g = load_graph(path)
+    own = _own_export(g, "translator")
+    if own is not None:
+        return own
     w = _Walker(g)
     raw: Dict[str, np.ndarray] = {}
     raw["tr.emb"] = _one(g, r"^embedding/embedding_lookup/\d+:0$")
