@@ -193,6 +193,17 @@ B200ASR_API int b200asr_stream_decoder_rows(b200asr_handle h, b200asr_stream st,
 B200ASR_API int b200asr_vad_create(const void* weight_blob, size_t blob_bytes, float ln_eps, int device, b200asr_handle* out);
 B200ASR_API int b200asr_vad_infer(b200asr_handle h, const float* wav_dev, int B, int N, int stride, float* logits_dev, void* stream);
 
+/* Session layer: the punctuation model.  Replaces the onnxruntime session of
+ * Inference/PythonInference/punc_recover/src/punc_recover.py:40-62 (`Punc.compile` / `Punc.punc_recover`: punc_recover/models/punc.onnx,
+ * inputs token ids i32 [1, U] (<S> characters </S>), padding mask, sinusoidal table; output f32 [1, U, 32] class probabilities).
+ *   weight blob  tensors emb [V, 64] (pre-scaled by sqrt(64)), pe [rows, 64], in / up / down / out .w [N, K] .b, l0..l4 .qkv.w [192, 64]
+ *                (1/sqrt(8) folded into the q rows) .qkv.b .o .f1 .f2 .ln1 .ln2, c0..c2 .w [64, 3 * 64] .b  (punc_model.punc_device_tensors)
+ *   ids_dev      [U] i32, one sentence without padding (the mask input of the graph is empty for a single sentence), U <= rows of pe
+ *   probs_dev    [U, 32] f32.  Exact fp32.  Synchronises `stream` (an id outside the table is an error).  Released with b200asr_destroy.
+ */
+B200ASR_API int b200asr_punc_create(const void* weight_blob, size_t blob_bytes, float ln_eps, int device, b200asr_handle* out);
+B200ASR_API int b200asr_punc_infer(b200asr_handle h, const int32_t* ids_dev, int U, float* probs_dev, void* stream);
+
 /* Roofline instrumentation (bench.py): time one stage of the schedule alone, `iters` launches bracketed by CUDA events on
  * `stream`; also returns that launch's algorithmic FLOPs and HBM bytes.  Run b200asr_recognize with the same (B, L) first. */
 enum { B200ASR_STAGE_CONV2 = 0, B200ASR_STAGE_FFN_W1 = 1, B200ASR_STAGE_FFN_W2 = 2, B200ASR_STAGE_STFT = 3,

@@ -55,6 +55,15 @@ def build(verbose: bool = False) -> bool:
     vad_src = os.path.join(REFERENCE, "Inference/PythonInference/vad/models/vad.onnx")
     if os.path.isfile(vad_src) and not os.path.isfile(os.path.join(REF, "models", "vad", "vad.onnx")):
         shutil.copyfile(vad_src, os.path.join(REF, "models", "vad", "vad.onnx"))
+    os.makedirs(os.path.join(REF, "models", "punc"), exist_ok=True)
+    punc_src = os.path.join(REFERENCE, "Inference/PythonInference/punc_recover/models/punc.onnx")
+    if os.path.isfile(punc_src) and not os.path.isfile(os.path.join(REF, "models", "punc", "punc.onnx")):
+        shutil.copyfile(punc_src, os.path.join(REF, "models", "punc", "punc.onnx"))
+    os.makedirs(os.path.join(REF, "dict"), exist_ok=True)
+    for f in ("lm_tokens_ch.txt", "lm_tokens_bd.txt"):
+        src_f = os.path.join(REFERENCE, "Inference/PythonInference/punc_recover/src/configs/dict", f)
+        if os.path.isfile(src_f) and not os.path.isfile(os.path.join(REF, "dict", f)):
+            shutil.copyfile(src_f, os.path.join(REF, "dict", f))
     # vocabulary files used by the reference's TextFeaturizer
     os.makedirs(os.path.join(REF, "dict"), exist_ok=True)
     for f in ("pinyin.txt", "lm_tokens.txt"):

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libb200asr.so")
-SOURCES = ["engine.cu", "frontend.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_chain.cu", "gemm_chain_pair.cu", "conv_sub_tc.cu", "chunk_ops.cu", "chunk_engine.cu", "vad_engine.cu", "block_ops.cu", "attention_tc.cu", "ctc_decode.cu", "ctc_beam.cu"]
+SOURCES = ["engine.cu", "frontend.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_chain.cu", "gemm_chain_pair.cu", "conv_sub_tc.cu", "chunk_ops.cu", "chunk_engine.cu", "vad_engine.cu", "punc_engine.cu", "block_ops.cu", "attention_tc.cu", "ctc_decode.cu", "ctc_beam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -65,6 +65,7 @@ size_t carve(b200asr_handle h, const Shapes& s, Buffers* b, char* base) {
 int ensure_workspace(b200asr_handle h, const Shapes& s, Buffers* b) {
   if (h->chunk) return fail(h, "this handle is a ChunkConformer engine: use the b200asr_stream_* entry points");
   if (h->vad) return fail(h, "this handle is a voice-activity model: use b200asr_vad_infer");
+  if (h->punc) return fail(h, "this handle is a punctuation model: use b200asr_punc_infer");
   size_t need = carve(h, s, b, nullptr);
   if (need > h->ws.bytes) {
     // growing the workspace invalidates captured graphs (they hold the old addresses)
@@ -499,6 +500,7 @@ B200ASR_API int b200asr_destroy(b200asr_handle h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->chunk) b200asr::chunk_model_free(h->chunk);
   if (h->vad) b200asr::vad_model_free(h->vad);
+  if (h->punc) b200asr::punc_model_free(h->punc);
   if (h->stage_wav) cudaFree(h->stage_wav);
   if (h->tr_ws) cudaFree(h->tr_ws);
   if (h->blob_dev) cudaFree(h->blob_dev);

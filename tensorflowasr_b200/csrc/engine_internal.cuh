@@ -56,6 +56,8 @@ struct ChunkModel;                                  // chunk_engine.cu: ChunkCon
 void chunk_model_free(ChunkModel* m);
 struct VadModel;                                    // vad_engine.cu: voice-activity model of the session layer
 void vad_model_free(VadModel* m);
+struct PuncModel;                                   // punc_engine.cu: punctuation model of the session layer
+void punc_model_free(PuncModel* m);
 int engine_alloc(const void* weight_blob, size_t blob_bytes, int device, const char* who, b200asr_engine** out);   // engine.cu
 int engine_init_frontend(b200asr_engine* h, const void* weight_blob);                                            // engine.cu
 }
@@ -111,6 +113,7 @@ struct b200asr_engine {
   size_t tr_ws_floats = 0;
   b200asr::ChunkModel* chunk = nullptr;   // set by b200asr_chunk_create: this handle is a ChunkConformer (state-cache streaming) engine
   b200asr::VadModel* vad = nullptr;       // set by b200asr_vad_create: this handle is the session layer's voice-activity model
+  b200asr::PuncModel* punc = nullptr;     // set by b200asr_punc_create: this handle is the session layer's punctuation model
   float* tap_dst = nullptr;
   int tap_count = 0, tap_max = 0;
 };

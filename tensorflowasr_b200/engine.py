@@ -79,6 +79,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200asr_debug_encode_taps.argtypes = [vp, vp, ci, ci, vp, ci, vp]
     lib.b200asr_vad_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, cf, ci, ctypes.POINTER(vp)]
     lib.b200asr_vad_infer.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.b200asr_punc_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, cf, ci, ctypes.POINTER(vp)]
+    lib.b200asr_punc_infer.argtypes = [vp, vp, ci, vp, vp]
     lib.b200asr_launch_count.restype = ctypes.c_int64
     lib.b200asr_launch_count.argtypes = [vp]
     _lib = lib

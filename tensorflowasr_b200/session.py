@@ -3,9 +3,9 @@
 Mirrors Inference/PythonInference/offline_asr_session.py (`ASRSession.send(wav_path)` -> one response per voiced segment, `OfflineVAD`)
 and stream_asr_session.py (`ASRSession.send(pcm_bytes)` / `final_send()` -> 'sentence begin' / 'inter break' / 'sentence end' events,
 `TaskContent`) with the same thresholds, time arithmetic and event dictionaries, so that a caller of the reference's sessions sees the
-same events.  The models behind it are this package's GPU engines (asr.ASR over libb200asr.so, vad_model.VAD over b200asr_vad_*);
-nothing here imports onnxruntime.  The punctuation model (punc_recover/) is not built: `punc` is an optional object with the
-reference's `punc_recover(text) -> list` method; without one the text is returned unpunctuated.
+same events.  The models behind it are this package's GPU engines (asr.ASR over libb200asr.so, vad_model.VAD over b200asr_vad_*,
+punc_model.Punc over b200asr_punc_*); nothing here imports onnxruntime.  `punc` is any object with the reference's
+`punc_recover(text) -> list` method; without one (None) the text is returned unpunctuated.
 
 Behaviours of the reference that are kept on purpose (they define what "the same events" means):
   * the offline segmenter never closes a segment on silence: its silence counter is fed only `if self.sound_pick` and nothing sets
@@ -388,9 +388,11 @@ def _resolve(cfg: dict, root: str):
     return cfg
 
 
-def sessions_from_reference_layout(root: str, kind: str = "offline", device: int = 0, model_root: Optional[str] = None):
+def sessions_from_reference_layout(root: str, kind: str = "offline", device: int = 0, model_root: Optional[str] = None,
+                                   with_punctuation: bool = True):
     """Build a session from the reference's deployment tree `root` (= Inference/PythonInference: asr/src/configs/am_data.yml,
-    asr/models/{offline,streaming}/*.onnx, vad/models/vad.onnx), as offline_asr_session.py:21-36 / stream_asr_session.py:20-37 do."""
+    asr/models/{offline,streaming}/*.onnx, vad/models/vad.onnx, punc_recover/models/punc.onnx + its configs), as
+    offline_asr_session.py:21-36 / stream_asr_session.py:20-37 do."""
     from . import asr as A
     from . import vad_model as V
     cfg = A.UserConfig(os.path.join(root, "asr/src/configs/am_data.yml"), os.path.join(root, "asr/src/configs/am_data.yml"))
@@ -399,5 +401,14 @@ def sessions_from_reference_layout(root: str, kind: str = "offline", device: int
     recogniser = A.ASR(cfg, device=device)
     recogniser.compile(os.path.join(model_root, "asr/models", kind), chunked=False)
     vad = V.VAD(model_path=os.path.join(model_root, "vad/models/vad.onnx"), device=device)
+    punc = None
+    punc_path = os.path.join(model_root, "punc_recover/models/punc.onnx")
+    if with_punctuation and os.path.isfile(punc_path):
+        from . import punc_model as P
+        pcfg = A.UserConfig(os.path.join(root, "punc_recover/src/configs/data.yml"), os.path.join(root, "punc_recover/src/configs/punc_settings.yml"))
+        for key in ("punc_vocab", "punc_biaodian"):
+            if not os.path.isabs(pcfg[key]["vocabulary"]):
+                pcfg[key]["vocabulary"] = os.path.normpath(os.path.join(root, pcfg[key]["vocabulary"]))
+        punc = P.Punc(pcfg, model_path=punc_path, device=device)
     cls = OfflineASRSession if kind == "offline" else StreamASRSession
-    return cls(recogniser, vad)
+    return cls(recogniser, vad, punc)

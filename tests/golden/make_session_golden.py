@@ -168,6 +168,34 @@ def scripted(off, stream):
     return out
 
 
+PUNC_TEXTS = ["甚至出现交易几乎停止的情况", "甚至出现交易几乎停制的情况甚至出现交易几乎品甚至出现交易几乎停制的情况甚至出现交易几乎挺",
+              "今天天气怎么样", "你好请问你叫什么名字我想知道明天会不会下雨如果下雨的话我们就不去公园了", "我",
+              "他说这个问题很难解决但是我们必须想办法因为时间已经不多了你觉得呢"]
+
+
+def punctuation(stream):
+    """punc_recover/src/punc_recover.py on a few sentences: token ids, the model's class probabilities, the punctuated token list."""
+    import importlib
+    pr = importlib.import_module("punc_recover.src.punc_recover")
+    from utils.user_config import UserConfig
+    cfg = UserConfig("./punc_recover/src/configs/data.yml", "./punc_recover/src/configs/punc_settings.yml")
+    punc = pr.Punc(cfg)
+    out, cases = {}, []
+    for i, txt in enumerate(PUNC_TEXTS):
+        x = [punc.vocab_featurizer.startid()] + punc.vocab_featurizer.extract(txt) + [punc.vocab_featurizer.endid()]
+        x = np.array([x], "int32")
+        names = [n.name for n in punc.model.get_inputs()]
+        probs = punc.model.run([punc.model.get_outputs()[0].name],
+                               input_feed={names[0]: x, names[1]: punc.creat_mask(x), names[2]: punc.pos_encode_inputs})[0]
+        out[f"punc{i}_ids"] = x[0]
+        out[f"punc{i}_probs"] = probs[0].astype(np.float32)
+        cases.append([txt, punc.punc_recover(txt)])
+        print("punc", "".join(cases[-1][1]))
+    out["punc_cases"] = np.frombuffer(json.dumps(cases, ensure_ascii=False).encode("utf-8"), dtype=np.uint8)
+    out["punc_pe"] = punc.pos_encode_inputs[0, :64].astype(np.float32)          # first rows of the positional table the caller feeds
+    return out
+
+
 def main():
     _install_stubs()
     os.chdir(REF)
@@ -223,6 +251,7 @@ def main():
         out[tag + "_events"] = np.frombuffer(json.dumps(events, ensure_ascii=False).encode("utf-8"), dtype=np.uint8)
         print(tag, json.dumps(events, ensure_ascii=False, indent=1))
     out.update(scripted(off, stream))
+    out.update(punctuation(stream))
     np.savez_compressed(os.path.join(ROOT, "tests/golden/session_golden.npz"), **out)
     print("segments", out["offline_segments"].tolist())
     print("responses", json.dumps(responses, ensure_ascii=False))

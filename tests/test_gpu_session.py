@@ -113,3 +113,51 @@ def test_offline_session_matches_reference(vad, gold, staged):
     segs = gold["offline_segments"]
     assert [[r["sentence_begin_time"], r["sentence_end_time"]] for r in resp] == [[int(s * 1000), int(e * 1000)] for s, e in segs]
     assert [r["best_text"] for r in resp] == _json(gold["offline_plain_text"])
+
+
+@pytest.fixture(scope="module")
+def punc(staged):
+    from tensorflowasr_b200 import punc_model as P
+    need = [os.path.join(staged.REF_DIR, "models", "punc", "punc.onnx"), os.path.join(staged.REF_DIR, "dict", "lm_tokens_ch.txt"),
+            os.path.join(staged.REF_DIR, "dict", "lm_tokens_bd.txt")]
+    if not all(os.path.isfile(p) for p in need):
+        pytest.skip("punctuation model / vocabularies not staged")
+    cfg = {"running_config": {}, "model_config": {"d_model": 64, "pe_input": 1024},
+           "punc_vocab": {"vocabulary": need[1], "blank_at_zero": True, "beam_width": 1},
+           "punc_biaodian": {"vocabulary": need[2], "blank_at_zero": True, "beam_width": 1}}
+    return P.Punc(cfg, model_path=need[0])
+
+
+def test_punctuation_matches_reference(punc, gold):
+    """b200asr_punc_infer vs the reference's Punc class on its onnxruntime: probabilities (1e-5) and the punctuated sentences."""
+    import torch
+    i = 0
+    while f"punc{i}_ids" in gold:
+        ids = torch.from_numpy(gold[f"punc{i}_ids"].astype(np.int32)).cuda()
+        got = punc.model.infer(ids).cpu().numpy()
+        assert np.abs(got - gold[f"punc{i}_probs"]).max() < 1e-5, i
+        i += 1
+    for txt, want in _json(gold["punc_cases"]):
+        assert punc.punc_recover(txt) == want
+    with pytest.raises(RuntimeError):
+        punc.model.infer(torch.tensor([1, 999999, 2], dtype=torch.int32, device="cuda"))
+    got = punc.model.infer(torch.from_numpy(gold["punc0_ids"].astype(np.int32)).cuda()).cpu().numpy()      # the handle survives the error
+    assert np.abs(got - gold["punc0_probs"]).max() < 1e-5
+
+
+def test_sessions_with_punctuation_match_reference(vad, punc, gold, staged):
+    """The complete sessions (VAD + recogniser + translator + punctuation), nothing on onnxruntime: the reference's own events."""
+    from tensorflowasr_b200 import session as S
+    sess = S.StreamASRSession(_asr(staged, "streaming"), vad, punc)
+    pcm = gold["pcm"]
+    got = []
+    for p in range(0, len(pcm), 160):
+        r = sess.send(pcm[p:p + 160].tobytes())
+        if r is not None:
+            got.append({"packet": p // 160, **r})
+    r = sess.final_send()
+    if r is not None:
+        got.append({"packet": -1, **r})
+    assert got == _json(gold["stream_events"])
+    off = S.OfflineASRSession(_asr(staged, "offline"), vad, punc)
+    assert off.send(pcm.astype(np.float32) / 32768) == _json(gold["offline_responses"])

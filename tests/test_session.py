@@ -132,3 +132,25 @@ def test_vad_oracle_is_pinned_to_the_reference(gold):
     dev = V.vad_device_tensors(raw)
     assert dev["c0.w"].shape == (80, 400) and dev["d4.w"].shape == (4, 80) and np.all(dev["d4.w"][1:] == 0)
     np.testing.assert_array_equal(dev["c0.w"][:, 80:160], raw["c0.w"][:, :, 1])
+
+
+def test_punctuation_oracle_is_pinned_to_the_reference(gold):
+    """oracle/punc_ref.py against the reference's Punc class on its own onnxruntime (golden 'punc*_probs'), and the importer's layout."""
+    from oracle import ort_ref, punc_ref
+    from tensorflowasr_b200 import punc_model as P
+    path = os.path.join(ort_ref.REF_DIR, "models", "punc", "punc.onnx")
+    if not os.path.isfile(path):
+        pytest.skip("oracle/_ref/models/punc/punc.onnx not staged (run oracle/build_ref.py)")
+    raw = P.import_punc(path)
+    pe = P.punc_positional_encoding()
+    np.testing.assert_array_equal(pe[:64], gold["punc_pe"])
+    i = 0
+    while f"punc{i}_ids" in gold:
+        y = punc_ref.punc_forward(raw, gold[f"punc{i}_ids"], pe)
+        assert np.abs(y - gold[f"punc{i}_probs"]).max() < 1e-5
+        i += 1
+    assert i >= 5
+    dev = P.punc_device_tensors(raw)
+    assert dev["l0.qkv.w"].shape == (192, 64) and dev["c1.w"].shape == (64, 192) and dev["up.w"].shape == (768, 64)
+    np.testing.assert_allclose(dev["l2.qkv.w"][:64], raw["l2.q.w"].T / np.sqrt(8.0), rtol=1e-6)
+    np.testing.assert_array_equal(dev["c0.w"][:, 64:128], raw["c0.w"][:, :, 1])
