@@ -1,0 +1,15 @@
+#!/bin/bash
+# A/B of a kernel change: GEMM + kernel tests, then bench config 2 with one and two batches in flight; prints the per-stage table
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/pytest_j.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_j.log | cut -c1-300
+for n in 1 2; do
+  timeout 600 python bench.py --inflight $n --steps 24 --warmup 3 --no-cpu-baseline --sustain 1 > gpurun_out/bench_j$n.json 2> gpurun_out/bench_j$n.err; echo "inflight $n rc=$?"
+done
+python - <<'PY'
+import json
+for n in (1,2):
+    try:
+        d=json.load(open(f"gpurun_out/bench_j{n}.json")); r=d["roofline"]
+        print(n, "ms/step", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["ms_per_step"],4), "ffn_chain", round(r["ms_per_launch"]*1e3,2), {k: round(v.get("ms_per_launch",0)*1e3,2) for k,v in r["other_stages"].items()})
+    except Exception as e: print(n, "ERR", e); print(open(f"gpurun_out/bench_j{n}.err").read()[-1500:])
+PY

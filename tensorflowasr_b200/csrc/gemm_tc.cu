@@ -26,9 +26,15 @@ using namespace tc;
 
 namespace {
 
-// pipeline depth: 4 stages, fewer when the LayerNorm epilogues' staging tile (BLOCK_M x BLOCK_N fp32) would not fit
+// pipeline depth: as many stages as fit beside the epilogue scratch, at most 6 (plain epilogues; the first `stages` weight slabs are
+// requested before griddepcontrol.wait, i.e. under the previous kernel's tail) / 4 (LayerNorm epilogues, whose staging tile
+// BLOCK_M x BLOCK_N fp32 shares the shared memory)
 __host__ __device__ constexpr int stages_for(bool is_ln, int bn, int bm) {
-  if (!is_ln) return 4;
+  if (!is_ln) {
+    for (int s = 6; s > 4; --s)
+      if (s * (bm + bn) * 128 + 4 * kWsmFloats * 4 + 1280 <= 226 * 1024) return s;
+    return 4;
+  }
   const int tile = bm * ((bn + 31) / 32) * 128;
   for (int s = 4; s >= 2; --s)
     if (s * (bm + bn) * 128 + tile <= 220 * 1024) return s;
