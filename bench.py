@@ -627,7 +627,7 @@ def main():
             timer.barrier()
             extra["single_batch_in_flight"] = {"ms_per_step": s0.elapsed_time(s1) / args.steps,
                                                "note": "same loop on one handle / one stream: what one batch costs when nothing else shares the GPU"}
-        e2e_run(max(args.warmup, 2), 0)
+        e2e_run(max(args.warmup, 2 * (len(pool) if kind in ("offline", "streaming") and pool is not None else 1)), 0)   # every (handle, pipeline slot) once: its graph is captured here
         timer.barrier()
         t0 = time.perf_counter()
         e2e_run(args.steps, 3)

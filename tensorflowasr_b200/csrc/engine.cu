@@ -196,12 +196,17 @@ int run_subsample_convs(Ctx& c, const float* mel, const Shapes& s, const Buffers
   c1.mel = mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
   c1.F1 = h->F1; c1.D = D; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
   c1.round_tf32 = (cfg.precision == B200ASR_PRECISION_TF32) ? 1 : 0;
-  h->launches++;
-  if (launch_conv1(c1, c.s)) return 1;
   GemmParams g{};
   g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = D; g.K = 9 * D; g.lda = 0; g.ldc = D;
   g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = D; g.pad_t = s.pt2; g.pad_f = s.pf2;
   g.round_out = 1;   // conv2's output is only read by the subsampling linear layer's GEMM (ignored by the fp32 kernel)
+  // tf32 mode: the conv1 map in fp16 (the first half of b.c1) and conv2 as kind::f16 -- the same 11-bit significands as tf32 operands
+  if (h->conv_f16 && tc_gemm_supported(g, EPI_BIAS_RELU)) {
+    g.f16 = 1;
+    if (tc_gemm_supported(g, EPI_BIAS_RELU)) { c1.out_f16 = 1; g.W = h->c2w16; } else g.f16 = 0;
+  }
+  h->launches++;
+  if (launch_conv1(c1, c.s)) return 1;
   h->launches++;
   if (cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(g, EPI_BIAS_RELU)) {
     if (launch_gemm_tc(h->tc, g, EPI_BIAS_RELU, c.s)) return 1;
@@ -450,6 +455,12 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
   h->linw = ok ? lookup(h, "sub.lin.w", (uint64_t)h->F2 * D * D, &ok) : nullptr;
   h->linb = ok ? lookup(h, "sub.lin.b", D, &ok) : nullptr;
   if (!ok) return bail(1);
+  {
+    auto it = h->tensors.find("sub.conv2.w16");
+    if (it != h->tensors.end() && it->second.second == 9ull * D * D / 2) h->c2w16 = it->second.first;
+    const char* off = getenv("B200ASR_NO_CONV_F16");
+    h->conv_f16 = h->c2w16 != nullptr && c.precision == B200ASR_PRECISION_TF32 && D % 8 == 0 && !(off && off[0] == '1');
+  }
   h->enc_blocks.resize(c.num_blocks);
   for (int i = 0; i < c.num_blocks; ++i)
     if (!load_block(h, "enc." + std::to_string(i) + ".", D, c.ff_dim, c.num_heads, c.head_size, c.kernel_size, &h->enc_blocks[i]))
@@ -937,10 +948,15 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
         g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = cfg.dmodel; g.K = 9 * cfg.dmodel;
         g.ldc = cfg.dmodel; g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = cfg.dmodel; g.pad_t = s.pt2;
         g.pad_f = s.pf2;
+        double in_bytes = 4.0;
+        if (h->conv_f16 && tc_gemm_supported(g, EPI_BIAS_RELU)) {   // (b.c1 holds the fp16 map the last recognize call left there)
+          g.f16 = 1;
+          if (tc_gemm_supported(g, EPI_BIAS_RELU)) { g.W = h->c2w16; in_bytes = 2.0; } else g.f16 = 0;
+        }
         if (cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(g, EPI_BIAS_RELU)) rc = launch_gemm_tc(h->tc, g, EPI_BIAS_RELU, st);
         else rc = launch_gemm_simt(g, EPI_BIAS_RELU, st);
         *flops = 2.0 * g.M * D * 9.0 * D;
-        *bytes = 4.0 * ((double)s.B * s.T1 * h->F1 * D + 9.0 * D * D + (double)g.M * D);
+        *bytes = in_bytes * ((double)s.B * s.T1 * h->F1 * D + 9.0 * D * D) + 4.0 * (double)g.M * D;
         break;
       }
       case B200ASR_STAGE_FFN_W1: {
@@ -1002,9 +1018,11 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
         Conv1Params c1{};
         c1.mel = b.mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
         c1.F1 = h->F1; c1.D = cfg.dmodel; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
+        c1.round_tf32 = (cfg.precision == B200ASR_PRECISION_TF32) ? 1 : 0;
+        c1.out_f16 = h->conv_f16 ? 1 : 0;
         rc = launch_conv1(c1, st);
         *flops = 2.0 * 9.0 * s.B * s.T1 * h->F1 * D;
-        *bytes = 4.0 * ((double)s.B * s.T * cfg.n_mels + (double)s.B * s.T1 * h->F1 * D);
+        *bytes = 4.0 * (double)s.B * s.T * cfg.n_mels + (h->conv_f16 ? 2.0 : 4.0) * (double)s.B * s.T1 * h->F1 * D;
         break;
       }
       case B200ASR_STAGE_DWCONV: {

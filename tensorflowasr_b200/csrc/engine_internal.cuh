@@ -75,6 +75,8 @@ struct b200asr_engine {
   int mel_nnz = 0;
   // subsampling
   const float *c1w, *c1b, *c2w, *c2b, *linw, *linb;
+  const float* c2w16 = nullptr;   // conv2 weights as IEEE fp16 (optional blob entry "sub.conv2.w16")
+  bool conv_f16 = false;          // tf32 mode: conv1 writes its map in fp16 and conv2 runs kind::f16 (B200ASR_NO_CONV_F16=1 turns it off)
   std::vector<BlockW> enc_blocks, ctc_blocks;
   const float *ctc_projw, *ctc_projb, *ctc_fcw, *ctc_fcb;
   int F1 = 0, F2 = 0;  // mel bins after conv1 / conv2

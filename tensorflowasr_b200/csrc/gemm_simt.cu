@@ -5,6 +5,7 @@
 // The A operand may be gathered on the fly as the im2col view of the second subsampling conv
 // (conformer_blocks.py:81-85: 3x3, stride 2, 'same'), so conv1's activations are read in place.
 #include "kernels.cuh"
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -244,6 +245,15 @@ __global__ void __launch_bounds__(256) conv1_f32x2_kernel(const Conv1Params p, i
       }
       const float2 lo = *reinterpret_cast<float2*>(&a_lo), hi = *reinterpret_cast<float2*>(&a_hi);
       float4 o4 = make_float4(fmaxf(lo.x, 0.f), fmaxf(lo.y, 0.f), fmaxf(hi.x, 0.f), fmaxf(hi.y, 0.f));
+      if (p.out_f16) {            // 4 halves = 8 bytes per thread; the row pointer counts halves here
+        __half2 h01 = __floats2half2_rn(o4.x, o4.y), h23 = __floats2half2_rn(o4.z, o4.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned int*>(&h01);
+        pk.y = *reinterpret_cast<unsigned int*>(&h23);
+        __half* hrow = reinterpret_cast<__half*>(p.out) + (((size_t)b * p.T1 + t1) * p.F1) * p.D + 4 * g;
+        *reinterpret_cast<uint2*>(hrow + (size_t)f1 * p.D) = pk;
+        continue;
+      }
       if (p.round_tf32) { o4.x = tf32_rn(o4.x); o4.y = tf32_rn(o4.y); o4.z = tf32_rn(o4.z); o4.w = tf32_rn(o4.w); }
       *reinterpret_cast<float4*>(orow + (size_t)f1 * p.D) = o4;
     }
@@ -280,6 +290,10 @@ int launch_conv1(const Conv1Params& p, cudaStream_t stream) {
   if (legacy < 0) {
     const char* e = getenv("B200ASR_CONV1_LEGACY");
     legacy = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (legacy && p.out_f16) {
+    snprintf(g_errbuf, sizeof(g_errbuf), "conv1: the legacy kernel (B200ASR_CONV1_LEGACY=1) has no fp16 output");
+    return 1;
   }
   if (!legacy) {
     B200_CUDA_OK(launch_k(conv1_f32x2_kernel, grid, dim3(threads), 2 * smem, stream, p, groups, flanes));

@@ -102,6 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();   // prologue resources are taken (TMEM allocated): the next kernel may start its own prologue
   const uint32_t a_rows_bytes = (p.a_mode == 1) ? (uint32_t)(p.bt * p.F2 * BLOCK_K * 4) : kABytes;
+  const int bk = p.f16 ? 2 * BLOCK_K : BLOCK_K;   // operand columns per 128-byte swizzle row (TMA coordinates count elements)
   // B operand = weights (constants): the first pipeline stages' weight slabs are requested BEFORE griddepcontrol.wait, under
   // the tail of the previous kernel; everything that kernel produced (A operand, residual) is touched only after the wait
   int b_prefetched = 0;
@@ -112,10 +113,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint8_t* sb = smem + kb * kStageBytes + kABytes;
       mbar_expect_tx(&full_bar[kb], a_rows_bytes + kBBytes);
       if (p.a_mode == 0) {
-        tma_load_2d(&map_b, &full_bar[kb], sb, kb * BLOCK_K, nt0 * BLOCK_N);
+        tma_load_2d(&map_b, &full_bar[kb], sb, kb * bk, nt0 * BLOCK_N);
       } else {
         const int tap = kb / p.kc, j = kb - tap * p.kc;
-        tma_load_2d(&map_b, &full_bar[kb], sb, tap * p.D + j * BLOCK_K, nt0 * BLOCK_N);
+        tma_load_2d(&map_b, &full_bar[kb], sb, tap * p.D + j * bk, nt0 * BLOCK_N);
       }
     }
   }
@@ -143,14 +144,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (b_done) --b_prefetched;
           else mbar_expect_tx(&full_bar[stage], a_rows_bytes + kBBytes);
           if (p.a_mode == 0) {
-            tma_load_2d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, mt * BLOCK_M);
-            if (!b_done) tma_load_2d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0);
+            tma_load_2d(&map_a, &full_bar[stage], sa, kb * bk, mt * BLOCK_M);
+            if (!b_done) tma_load_2d(&map_b, &full_bar[stage], sb, kb * bk, n0);
           } else {
             const int b = mt / p.tiles_per_b, tb = mt - b * p.tiles_per_b;
             const int tap = kb / p.kc, j = kb - tap * p.kc;
             const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(&map_a, &full_bar[stage], sa, j * BLOCK_K, kw - p.pad_f, 2 * tb * p.bt + kh - p.pad_t, b);
-            if (!b_done) tma_load_2d(&map_b, &full_bar[stage], sb, tap * p.D + j * BLOCK_K, n0);
+            tma_load_4d(&map_a, &full_bar[stage], sa, j * bk, kw - p.pad_f, 2 * tb * p.bt + kh - p.pad_t, b);
+            if (!b_done) tma_load_2d(&map_b, &full_bar[stage], sb, tap * p.D + j * bk, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -158,13 +159,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    const uint32_t idesc = p.f16 ? make_idesc_f16(BLOCK_M, BLOCK_N) : make_idesc(BLOCK_M, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
     const int kdim = (p.a_mode == 0) ? p.K : p.D;                       // columns covered by the slabs of one K run
-    const int tail_cols = kdim - (kdim / BLOCK_K) * BLOCK_K;
-    const int tail_ksteps = tail_cols == 0 ? BLOCK_K / UMMA_K : (tail_cols + UMMA_K - 1) / UMMA_K;
+    const int umma_k = p.f16 ? 2 * UMMA_K : UMMA_K;                       // columns per instruction (32 bytes of a swizzle row either way)
+    const int tail_cols = kdim - (kdim / bk) * bk;
+    const int tail_ksteps = tail_cols == 0 ? BLOCK_K / UMMA_K : (tail_cols + umma_k - 1) / umma_k;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -186,7 +188,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in the 16-byte address field
-            if (k < ksteps) umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (k < ksteps) {
+              if (p.f16) umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           tcgen05_commit(&empty_bar[stage]);                           // frees this smem stage when the MMAs retire
           if (kb == p.num_k_blocks - 1) tcgen05_commit(&tmem_full[acc]);  // accumulator complete
@@ -349,6 +354,7 @@ bool tc_gemm_supported(const GemmParams& p, int epilogue) {
   }
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W) | reinterpret_cast<uintptr_t>(p.C)) & 15) return false;
   if (p.a_mode == 0) return (p.lda % 4) == 0;
+  if (p.f16 && (p.D % 8) != 0) return false;                 // 16-byte global strides of the fp16 map
   return p.F2 <= 64 && p.F2 >= 1 && (128 / p.F2) >= 1 && (p.D % 4) == 0 && p.N == p.D && 2 * p.F2 <= 256;
 }
 
@@ -364,13 +370,17 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   tp.num_n_tiles = ceil_div(p.N, bn);
   tp.a_mode = p.a_mode;
   tp.round_out = p.round_out;
+  tp.f16 = (p.f16 && p.a_mode == 1) ? 1 : 0;
+  const bool f16 = tp.f16 != 0;
+  const cuuint64_t esz = f16 ? 2 : 4;                       // operand element size
+  const cuuint32_t bk = f16 ? 2 * BLOCK_K : BLOCK_K;         // operand columns per 128-byte swizzle row
   CUtensorMap ma, mb;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.K * 4};
-    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
-    if (encode_map(ctx, &mb, p.W, 2, dims, strides, box, ones)) return 1;
+    const cuuint64_t strides[1] = {(cuuint64_t)p.K * esz};
+    const cuuint32_t box[2] = {bk, (cuuint32_t)bn};
+    if (encode_map(ctx, &mb, p.W, 2, dims, strides, box, ones, f16)) return 1;
   }
   // M tile: 128 rows normally; 64 when 128-row tiles would leave most SMs idle (the 8000-row, N<=256 GEMMs of one batch)
   int bm = 128;
@@ -386,15 +396,15 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     const int B = p.M / (p.T2 * p.F2);
     tp.T2 = p.T2; tp.F2 = p.F2; tp.D = p.D; tp.pad_t = p.pad_t; tp.pad_f = p.pad_f;
     tp.bt = 128 / p.F2;
-    tp.kc = ceil_div(p.D, BLOCK_K);
+    tp.kc = ceil_div(p.D, (int)bk);
     tp.tiles_per_b = ceil_div(p.T2, tp.bt);
     tp.num_m_tiles = B * tp.tiles_per_b;
     tp.num_k_blocks = 9 * tp.kc;
     const cuuint64_t dims[4] = {(cuuint64_t)p.D, (cuuint64_t)p.F1, (cuuint64_t)p.T1, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)p.D * 4, (cuuint64_t)p.F1 * p.D * 4, (cuuint64_t)p.T1 * p.F1 * p.D * 4};
-    const cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(2 * p.F2), (cuuint32_t)(2 * tp.bt), 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.D * esz, (cuuint64_t)p.F1 * p.D * esz, (cuuint64_t)p.T1 * p.F1 * p.D * esz};
+    const cuuint32_t box[4] = {bk, (cuuint32_t)(2 * p.F2), (cuuint32_t)(2 * tp.bt), 1};
     const cuuint32_t estr[4] = {1, 2, 2, 1};
-    if (encode_map(ctx, &ma, p.A, 4, dims, strides, box, estr)) return 1;
+    if (encode_map(ctx, &ma, p.A, 4, dims, strides, box, estr, f16)) return 1;
   }
   // LayerNorm epilogues: residual-in / output tiles travel by TMA ([M, N] in BLOCK_M x 32-column slabs; stores clip tails)
   CUtensorMap lnmaps[3];

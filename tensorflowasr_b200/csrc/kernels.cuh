@@ -31,6 +31,7 @@ struct Conv1Params {
   float* out;         // [B, T1, F1, D]
   int B, T, F, T1, F1, D, pad_t, pad_f;
   int round_tf32 = 0;   // 1: outputs rounded to nearest tf32 (they feed conv2's tensor-core A operand only)
+  int out_f16 = 0;      // 1: `out` holds IEEE fp16 [B, T1, F1, D] (same 11-bit significand as tf32, half the bytes; conv2 then runs kind::f16)
 };
 int launch_conv1(const Conv1Params& p, cudaStream_t stream);
 
@@ -70,6 +71,9 @@ struct GemmParams {
   // tcgen05 path: store C (plain epilogues) / C2 (LayerNorm epilogues) rounded to nearest tf32 -- set when the tensor is only
   // read as a tensor-core operand again (the datapath would truncate raw fp32 bits)
   int round_out = 0;
+  // tcgen05 path, a_mode 1 only: A (the conv1 map) and W hold IEEE fp16 -- products of 11-bit significands accumulated in fp32, exactly
+  // what kind::tf32 computes on tf32-rounded operands, at twice the MMA rate and half the operand bytes
+  int f16 = 0;
 };
 int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream);
 

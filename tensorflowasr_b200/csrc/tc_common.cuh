@@ -31,6 +31,7 @@ struct TcParams {
   // conv2 implicit GEMM
   int a_mode, T2, F2, D, bt, kc, pad_t, pad_f, tiles_per_b;
   int round_out;   // plain epilogues: store C rounded to nearest tf32 (it is only read as a tensor-core operand again)
+  int f16;         // A and B operands hold IEEE fp16 (kind::f16, 64 columns per 128-byte swizzle row, K = 16 per instruction)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -93,6 +94,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// the same with fp16 operands (kind::f16: K = 16 per instruction = the same 32 bytes of a swizzle row)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -106,6 +117,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29) (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D=f32, A=B=f16 (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // SFU-approximate activations for the tensor-core path (ex2.approx + rcp.approx, ~1e-6 relative: far below tf32 input rounding)
@@ -518,9 +533,9 @@ __device__ __forceinline__ void epilogue_ln_tma(const TcParams& p, uint32_t tadd
 using EncodeTiledFn = PFN_cuTensorMapEncodeTiled_v12000;
 
 inline int encode_map(TcContext& ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-               const cuuint32_t* box, const cuuint32_t* estr) {
+               const cuuint32_t* box, const cuuint32_t* estr, bool f16 = false) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx.encode_tiled);
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

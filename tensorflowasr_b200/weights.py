@@ -685,6 +685,12 @@ def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_g
         for k in out:
             if k.endswith(_TC_OPERAND_SUFFIXES) or k in _TC_OPERAND_NAMES or k == "tr.fc.w":
                 out[k] = round_to_tf32(out[k])
+        # conv2's weights once more as IEEE fp16, two per float32 word: fp16 carries the same 11-bit significand as tf32, so the
+        # subsampler's second convolution runs kind::f16 on an fp16 conv1 map with unchanged products (half the operand bytes, twice
+        # the MMA rate).  Left out when a weight would overflow or fall into fp16's subnormal range by more than the odd tiny value.
+        w16 = out["sub.conv2.w"].astype(np.float16)
+        if np.isfinite(w16).all() and (D * 9 * D) % 2 == 0:
+            out["sub.conv2.w16"] = np.ascontiguousarray(w16).view(np.float32).reshape(-1)
     return out
 
 
