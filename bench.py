@@ -704,7 +704,10 @@ def main():
                            "seq_len": Ls, "parallelism": f"dp{world} (utterance shard, one async all_gather of ids+lengths per step)",
                            "l2_policy": (f"{NROT} distinct input batches rotated ({NROT * B_local * Ls * 4 / 1e6:.0f} MB > 126 MB L2)" if kind != "chunk" else
                                          "every step reads a new 320 ms chunk per stream; caches + weights (~140 MB) exceed L2"),
-                           "frame": "10 ms hop (160 samples)", "batches_in_flight": (args.inflight if kind in ("offline", "streaming") else 1)},
+                           "frame": "10 ms hop (160 samples)", "batches_in_flight": (args.inflight if kind in ("offline", "streaming") else 1),
+                           "operands": ("tf32 tensor-core operands, fp32 accumulate and fp32 activations in HBM; the subsampler's conv1 map and conv2 output are "
+                                        "stored as IEEE fp16 (the same 11-bit significand as tf32) and its two GEMMs run kind::f16" if args.precision == "tf32" and kind != "chunk"
+                                        else ("tf32 tensor-core operands, fp32 accumulate" if args.precision == "tf32" else "fp32 CUDA cores"))},
                 "e2e": {"value": frames_step * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py tests/test_gpu_reference_sized.py -m gpu -q -x > gpurun_out/pytest_j.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_j.log | cut -c1-400
 timeout 600 python bench.py --inflight 1 --steps 24 --warmup 3 --no-cpu-baseline --sustain 1 > gpurun_out/bench_j1.json 2> gpurun_out/bench_j1.err; echo "inflight 1 rc=$?"
 timeout 600 python bench.py --inflight 2 --steps 24 --warmup 3 --no-cpu-baseline --sustain 1 > gpurun_out/bench_j2.json 2> gpurun_out/bench_j2.err; echo "inflight 2 rc=$?"
-B200ASR_NO_CONV_F16=1 timeout 600 python bench.py --inflight 1 --steps 24 --warmup 3 --no-cpu-baseline --sustain 1 > gpurun_out/bench_j3.json 2> gpurun_out/bench_j3.err; echo "inflight 1, fp32 conv1 map rc=$?"
+B200ASR_NO_CONV_F16=2 timeout 600 python bench.py --inflight 1 --steps 24 --warmup 3 --no-cpu-baseline --sustain 1 > gpurun_out/bench_j3.json 2> gpurun_out/bench_j3.err; echo "inflight 1, fp32 conv1 map rc=$?"
 timeout 600 python bench.py --config 3 --steps 10 --warmup 3 --no-cpu-baseline --sustain 1 > gpurun_out/bench_j4.json 2> gpurun_out/bench_j4.err; echo "config 3 rc=$?"
 python - <<'PY'
 import json

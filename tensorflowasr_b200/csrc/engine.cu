@@ -179,7 +179,40 @@ int run_encoder(Ctx& c, const float* wav, const Shapes& s, const Buffers& b) {
   return run_encoder_tail(c, s, b);
 }
 
-// mel [B, T, n_mels] -> b.c2 = relu(conv2(relu(conv1(mel))))  [B, T2, F2, D]
+// the subsampling linear layer as an fp16-operand GEMM with fused LayerNorm (conv2 then writes fp16)
+GemmParams sublin_params(b200asr_handle h, const Shapes& s, const Buffers& b, bool f16) {
+  const b200asr_config& cfg = h->cfg;
+  const int D = cfg.dmodel;
+  GemmParams lp{};
+  lp.A = b.c2; lp.W = f16 ? h->linw16 : h->linw; lp.bias = h->linb; lp.C = b.x; lp.C2 = b.xn; lp.M = s.M; lp.N = D; lp.K = h->F2 * D;
+  lp.lda = h->F2 * D; lp.ldc = D; lp.ln_eps = cfg.ln_eps; lp.f16 = f16 ? 1 : 0;
+  if (!h->enc_blocks.empty()) { lp.ln1_g = h->enc_blocks[0].ffn1.ln.g; lp.ln1_b = h->enc_blocks[0].ffn1.ln.b; }
+  return lp;
+}
+GemmParams conv2_params(b200asr_handle h, const Shapes& s, const Buffers& b) {
+  const int D = h->cfg.dmodel;
+  GemmParams g{};
+  g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = D; g.K = 9 * D; g.lda = 0; g.ldc = D;
+  g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = D; g.pad_t = s.pt2; g.pad_f = s.pf2;
+  g.round_out = 1;   // conv2's output is only read by the subsampling linear layer's GEMM (ignored by the fp32 kernel)
+  return g;
+}
+// How the two-kernel subsampler runs (one decision, taken the same way by every stage that touches b.c1 / b.c2):
+//   0  fp32 maps (exact-fp32 mode, or fp16 switched off)
+//   1  conv1 map in fp16, conv2 kind::f16, conv2's output fp32
+//   2  ... and conv2's output in fp16, read by the subsampling linear layer as an fp16-operand GEMM with fused LayerNorm
+int sub_f16_mode(b200asr_handle h, const Shapes& s, const Buffers& b) {
+  if (!h->conv_f16 || h->cfg.precision != B200ASR_PRECISION_TF32 || h->use_fused_sub) return 0;
+  GemmParams g = conv2_params(h, s, b);
+  g.f16 = 1; g.W = h->c2w16;
+  if (!tc_gemm_supported(g, EPI_BIAS_RELU)) return 0;
+  if (!h->sub_out_f16 || !fused_ln_ok(h) || h->enc_blocks.empty()) return 1;
+  g.out_f16 = 1;
+  if (!tc_gemm_supported(g, EPI_BIAS_RELU) || !tc_gemm_supported(sublin_params(h, s, b, true), EPI_BIAS_LN)) return 1;
+  return 2;
+}
+
+// mel [B, T, n_mels] -> b.c2 = relu(conv2(relu(conv1(mel))))  [B, T2, F2, D]  (fp16 in sub_f16_mode 2, else fp32)
 int run_subsample_convs(Ctx& c, const float* mel, const Shapes& s, const Buffers& b) {
   b200asr_handle h = c.h;
   const b200asr_config& cfg = h->cfg;
@@ -196,15 +229,10 @@ int run_subsample_convs(Ctx& c, const float* mel, const Shapes& s, const Buffers
   c1.mel = mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
   c1.F1 = h->F1; c1.D = D; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
   c1.round_tf32 = (cfg.precision == B200ASR_PRECISION_TF32) ? 1 : 0;
-  GemmParams g{};
-  g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = D; g.K = 9 * D; g.lda = 0; g.ldc = D;
-  g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = D; g.pad_t = s.pt2; g.pad_f = s.pf2;
-  g.round_out = 1;   // conv2's output is only read by the subsampling linear layer's GEMM (ignored by the fp32 kernel)
-  // tf32 mode: the conv1 map in fp16 (the first half of b.c1) and conv2 as kind::f16 -- the same 11-bit significands as tf32 operands
-  if (h->conv_f16 && tc_gemm_supported(g, EPI_BIAS_RELU)) {
-    g.f16 = 1;
-    if (tc_gemm_supported(g, EPI_BIAS_RELU)) { c1.out_f16 = 1; g.W = h->c2w16; } else g.f16 = 0;
-  }
+  GemmParams g = conv2_params(h, s, b);
+  const int mode = sub_f16_mode(h, s, b);
+  if (mode >= 1) { c1.out_f16 = 1; g.f16 = 1; g.W = h->c2w16; }
+  if (mode == 2) g.out_f16 = 1;
   h->launches++;
   if (launch_conv1(c1, c.s)) return 1;
   h->launches++;
@@ -222,9 +250,8 @@ int run_encoder_tail(Ctx& c, const Shapes& s, const Buffers& b) {
   const b200asr_config& cfg = h->cfg;
   const int D = cfg.dmodel;
   if (fused_ln_ok(h) && !h->enc_blocks.empty()) {
-    GemmParams lp{};
-    lp.A = b.c2; lp.W = h->linw; lp.bias = h->linb; lp.C = b.x; lp.C2 = b.xn; lp.M = s.M; lp.N = D; lp.K = h->F2 * D;
-    lp.lda = h->F2 * D; lp.ldc = D; lp.ln1_g = h->enc_blocks[0].ffn1.ln.g; lp.ln1_b = h->enc_blocks[0].ffn1.ln.b; lp.ln_eps = cfg.ln_eps;
+    // (the same predicate run_subsample_convs used when it chose conv2's output type)
+    GemmParams lp = sublin_params(h, s, b, sub_f16_mode(h, s, b) == 2);
     if (gemm_p(c, lp, EPI_BIAS_LN)) return 1;
     if (tap(c, b.x, (size_t)s.M * D)) return 1;
     for (size_t i = 0; i < h->enc_blocks.size(); ++i) {
@@ -460,6 +487,9 @@ B200ASR_API int b200asr_create(const void* weight_blob, size_t blob_bytes, const
     if (it != h->tensors.end() && it->second.second == 9ull * D * D / 2) h->c2w16 = it->second.first;
     const char* off = getenv("B200ASR_NO_CONV_F16");
     h->conv_f16 = h->c2w16 != nullptr && c.precision == B200ASR_PRECISION_TF32 && D % 8 == 0 && !(off && off[0] == '1');
+    auto il = h->tensors.find("sub.lin.w16");
+    if (il != h->tensors.end() && il->second.second == (uint64_t)h->F2 * D * D / 2) h->linw16 = il->second.first;
+    h->sub_out_f16 = h->conv_f16 && h->linw16 != nullptr && !(off && off[0] == '2');   // (needs the fused-LayerNorm GEMM too: checked where it is used)
   }
   h->enc_blocks.resize(c.num_blocks);
   for (int i = 0; i < c.num_blocks; ++i)
@@ -944,19 +974,15 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
           *bytes = 4.0 * ((double)s.B * s.T * cfg.n_mels + 9.0 * D * D + (double)s.B * s.T2 * h->F2 * D);
           break;
         }
-        GemmParams g{};
-        g.A = b.c1; g.W = h->c2w; g.bias = h->c2b; g.C = b.c2; g.M = s.B * s.T2 * h->F2; g.N = cfg.dmodel; g.K = 9 * cfg.dmodel;
-        g.ldc = cfg.dmodel; g.a_mode = 1; g.T1 = s.T1; g.F1 = h->F1; g.T2 = s.T2; g.F2 = h->F2; g.D = cfg.dmodel; g.pad_t = s.pt2;
-        g.pad_f = s.pf2;
-        double in_bytes = 4.0;
-        if (h->conv_f16 && tc_gemm_supported(g, EPI_BIAS_RELU)) {   // (b.c1 holds the fp16 map the last recognize call left there)
-          g.f16 = 1;
-          if (tc_gemm_supported(g, EPI_BIAS_RELU)) { g.W = h->c2w16; in_bytes = 2.0; } else g.f16 = 0;
-        }
+        GemmParams g = conv2_params(h, s, b);
+        const int mode = sub_f16_mode(h, s, b);     // (b.c1 holds the map the last recognize call left there, in this very format)
+        if (mode >= 1) { g.f16 = 1; g.W = h->c2w16; }
+        if (mode == 2) g.out_f16 = 1;
+        const double in_bytes = mode >= 1 ? 2.0 : 4.0, out_bytes = mode == 2 ? 2.0 : 4.0;
         if (cfg.precision == B200ASR_PRECISION_TF32 && tc_gemm_supported(g, EPI_BIAS_RELU)) rc = launch_gemm_tc(h->tc, g, EPI_BIAS_RELU, st);
         else rc = launch_gemm_simt(g, EPI_BIAS_RELU, st);
         *flops = 2.0 * g.M * D * 9.0 * D;
-        *bytes = in_bytes * ((double)s.B * s.T1 * h->F1 * D + 9.0 * D * D) + 4.0 * (double)g.M * D;
+        *bytes = in_bytes * ((double)s.B * s.T1 * h->F1 * D + 9.0 * D * D) + out_bytes * (double)g.M * D;
         break;
       }
       case B200ASR_STAGE_FFN_W1: {
@@ -980,10 +1006,15 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
         break;
       }
       case B200ASR_STAGE_SUBLIN: {
-        rc = gemm(c, b.c2, h->F2 * cfg.dmodel, h->linw, h->linb, nullptr, 0.f, b.xn, cfg.dmodel, s.M, cfg.dmodel, h->F2 * cfg.dmodel,
-                  EPI_BIAS);
+        const bool lin16 = sub_f16_mode(h, s, b) == 2;            // (b.c2 holds what conv2 wrote last: fp16 then)
+        if (fused_ln_ok(h) && !h->enc_blocks.empty()) {          // the schedule's own launch: bias + LayerNorm fused, writes b.x and b.xn
+          GemmParams lp = sublin_params(h, s, b, lin16);
+          rc = gemm_p(c, lp, EPI_BIAS_LN);
+        } else {
+          rc = gemm(c, b.c2, h->F2 * cfg.dmodel, h->linw, h->linb, nullptr, 0.f, b.xn, cfg.dmodel, s.M, cfg.dmodel, h->F2 * cfg.dmodel, EPI_BIAS);
+        }
         *flops = 2.0 * M * D * h->F2 * D;
-        *bytes = 4.0 * (M * h->F2 * D + D * h->F2 * D + M * D);
+        *bytes = (lin16 ? 2.0 : 4.0) * (M * h->F2 * D + D * h->F2 * D) + 4.0 * 2.0 * M * D;
         break;
       }
       case B200ASR_STAGE_ATTENTION: {
@@ -1019,10 +1050,10 @@ B200ASR_API int b200asr_time_stage(b200asr_handle h, int stage, int B, int L, in
         c1.mel = b.mel; c1.w = h->c1w; c1.bias = h->c1b; c1.out = b.c1; c1.B = s.B; c1.T = s.T; c1.F = cfg.n_mels; c1.T1 = s.T1;
         c1.F1 = h->F1; c1.D = cfg.dmodel; c1.pad_t = s.pt1; c1.pad_f = s.pf1;
         c1.round_tf32 = (cfg.precision == B200ASR_PRECISION_TF32) ? 1 : 0;
-        c1.out_f16 = h->conv_f16 ? 1 : 0;
+        c1.out_f16 = sub_f16_mode(h, s, b) >= 1 ? 1 : 0;
         rc = launch_conv1(c1, st);
         *flops = 2.0 * 9.0 * s.B * s.T1 * h->F1 * D;
-        *bytes = 4.0 * (double)s.B * s.T * cfg.n_mels + (h->conv_f16 ? 2.0 : 4.0) * (double)s.B * s.T1 * h->F1 * D;
+        *bytes = 4.0 * (double)s.B * s.T * cfg.n_mels + (c1.out_f16 ? 2.0 : 4.0) * (double)s.B * s.T1 * h->F1 * D;
         break;
       }
       case B200ASR_STAGE_DWCONV: {
@@ -1123,7 +1154,11 @@ B200ASR_API int b200asr_debug_subsample_convs(b200asr_handle h, const float* mel
   Buffers b;
   if (ensure_workspace(h, s, &b)) return 1;
   Ctx c{h, static_cast<cudaStream_t>(stream)};
-  ENG_TRY(h, run_subsample_convs(c, mel_dev, s, b));
+  const bool keep = h->sub_out_f16;
+  h->sub_out_f16 = false;                   // the hook returns conv2's map as fp32 (the conv1 map may still be fp16)
+  const int rc_convs = run_subsample_convs(c, mel_dev, s, b);
+  h->sub_out_f16 = keep;
+  ENG_TRY(h, rc_convs);
   ENG_CUDA(h, cudaMemcpyAsync(out_dev, b.c2, sizeof(float) * (size_t)s.B * s.T2 * h->F2 * h->cfg.dmodel, cudaMemcpyDeviceToDevice, c.s));
   return 0;
 }

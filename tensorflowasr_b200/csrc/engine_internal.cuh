@@ -75,8 +75,9 @@ struct b200asr_engine {
   int mel_nnz = 0;
   // subsampling
   const float *c1w, *c1b, *c2w, *c2b, *linw, *linb;
-  const float* c2w16 = nullptr;   // conv2 weights as IEEE fp16 (optional blob entry "sub.conv2.w16")
+  const float *c2w16 = nullptr, *linw16 = nullptr;   // conv2 / subsampling-linear weights as IEEE fp16 (optional blob entries "sub.conv2.w16", "sub.lin.w16")
   bool conv_f16 = false;          // tf32 mode: conv1 writes its map in fp16 and conv2 runs kind::f16 (B200ASR_NO_CONV_F16=1 turns it off)
+  bool sub_out_f16 = false;       // ... and conv2 writes ITS output in fp16 for an fp16-operand subsampling linear layer (B200ASR_NO_CONV_F16=2 turns only this off)
   std::vector<BlockW> enc_blocks, ctc_blocks;
   const float *ctc_projw, *ctc_projb, *ctc_fcw, *ctc_fcb;
   int F1 = 0, F2 = 0;  // mel bins after conv1 / conv2

@@ -42,7 +42,7 @@ __host__ __device__ constexpr int stages_for(bool is_ln, int bn, int bm) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int EPI, int BLOCK_N, int BLOCK_M>
+template <int EPI, int BLOCK_N, int BLOCK_M, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c,
@@ -102,7 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();   // prologue resources are taken (TMEM allocated): the next kernel may start its own prologue
   const uint32_t a_rows_bytes = (p.a_mode == 1) ? (uint32_t)(p.bt * p.F2 * BLOCK_K * 4) : kABytes;
-  const int bk = p.f16 ? 2 * BLOCK_K : BLOCK_K;   // operand columns per 128-byte swizzle row (TMA coordinates count elements)
+  constexpr int bk = F16 ? 2 * BLOCK_K : BLOCK_K;   // operand columns per 128-byte swizzle row (TMA coordinates count elements)
   // B operand = weights (constants): the first pipeline stages' weight slabs are requested BEFORE griddepcontrol.wait, under
   // the tail of the previous kernel; everything that kernel produced (A operand, residual) is touched only after the wait
   int b_prefetched = 0;
@@ -159,12 +159,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    const uint32_t idesc = p.f16 ? make_idesc_f16(BLOCK_M, BLOCK_N) : make_idesc(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N) : make_idesc(BLOCK_M, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
     const int kdim = (p.a_mode == 0) ? p.K : p.D;                       // columns covered by the slabs of one K run
-    const int umma_k = p.f16 ? 2 * UMMA_K : UMMA_K;                       // columns per instruction (32 bytes of a swizzle row either way)
+    constexpr int umma_k = F16 ? 2 * UMMA_K : UMMA_K;                     // columns per instruction (32 bytes of a swizzle row either way)
     const int tail_cols = kdim - (kdim / bk) * bk;
     const int tail_ksteps = tail_cols == 0 ? BLOCK_K / UMMA_K : (tail_cols + umma_k - 1) / umma_k;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -189,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in the 16-byte address field
             if (k < ksteps) {
-              if (p.f16) umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if constexpr (F16) umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
               else umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
@@ -264,11 +264,11 @@ constexpr size_t smem_bytes() {
          1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-template <int EPI, int BLOCK_N, int BLOCK_M>
+template <int EPI, int BLOCK_N, int BLOCK_M, bool F16 = false>
 int launch_one(TcContext& ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap* lnmaps, const TcParams& tp,
                cudaStream_t stream) {
   static PerDeviceSmem configured;
-  auto kern = gemm_tc_kernel<EPI, BLOCK_N, BLOCK_M>;
+  auto kern = gemm_tc_kernel<EPI, BLOCK_N, BLOCK_M, F16>;
   if (configured.need(smem_bytes<EPI, BLOCK_N, BLOCK_M>()))
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<EPI, BLOCK_N, BLOCK_M>()));
   const int tiles = tp.num_m_tiles * tp.num_n_tiles;
@@ -345,6 +345,11 @@ int tc_argmax_tiles(int N) { return ceil_div(N, pick_block_n(N, EPI_BIAS_ARGMAX,
 
 bool tc_gemm_supported(const GemmParams& p, int epilogue) {
   if (p.M <= 0 || p.N % 4 != 0 || p.K % 4 != 0) return false;
+  if (p.f16) {   // fp16 operands: conv2 (a_mode 1, bias + ReLU) and the subsampling linear layer (a_mode 0, bias + LayerNorm), N = 144 | 256
+    if (!(p.N == 144 || p.N == 256)) return false;
+    if (p.a_mode == 1 ? epilogue != EPI_BIAS_RELU : (epilogue != EPI_BIAS_LN || p.lda % 8 != 0 || p.K % 8 != 0)) return false;
+  }
+  if (p.out_f16 && (epi_is_ln(epilogue) || epilogue == EPI_GLU || epilogue == EPI_BIAS_ARGMAX || epilogue == EPI_RESID || p.ldc % 4 != 0)) return false;
   if (epilogue == EPI_GLU && p.N % 8 != 0) return false;
   if (epilogue == EPI_BIAS_ARGMAX && (p.a_mode != 0 || p.bias == nullptr)) return false;
   if (epi_is_ln(epilogue)) {
@@ -370,7 +375,8 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   tp.num_n_tiles = ceil_div(p.N, bn);
   tp.a_mode = p.a_mode;
   tp.round_out = p.round_out;
-  tp.f16 = (p.f16 && p.a_mode == 1) ? 1 : 0;
+  tp.f16 = p.f16 ? 1 : 0;
+  tp.out_f16 = p.out_f16 ? 1 : 0;
   const bool f16 = tp.f16 != 0;
   const cuuint64_t esz = f16 ? 2 : 4;                       // operand element size
   const cuuint32_t bk = f16 ? 2 * BLOCK_K : BLOCK_K;         // operand columns per 128-byte swizzle row
@@ -387,11 +393,11 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
   if (p.a_mode == 0 && bn != 224 && epilogue != EPI_BIAS_ARGMAX && ceil_div(p.M, 128) * tp.num_n_tiles < (ctx.num_sms * 3) / 4) bm = 64;
   if (p.a_mode == 0) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 4};
-    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bm};
-    if (encode_map(ctx, &ma, p.A, 2, dims, strides, box, ones)) return 1;
+    const cuuint64_t strides[1] = {(cuuint64_t)p.lda * esz};
+    const cuuint32_t box[2] = {bk, (cuuint32_t)bm};
+    if (encode_map(ctx, &ma, p.A, 2, dims, strides, box, ones, f16)) return 1;
     tp.num_m_tiles = ceil_div(p.M, bm);
-    tp.num_k_blocks = ceil_div(p.K, BLOCK_K);
+    tp.num_k_blocks = ceil_div(p.K, (int)bk);
   } else {
     const int B = p.M / (p.T2 * p.F2);
     tp.T2 = p.T2; tp.F2 = p.F2; tp.D = p.D; tp.pad_t = p.pad_t; tp.pad_f = p.pad_f;
@@ -416,6 +422,16 @@ int launch_gemm_tc(TcContext& ctx, const GemmParams& p, int epilogue, cudaStream
     if (p.resid && encode_map(ctx, &lnmaps[0], p.resid, 2, dims, strides, box, ones)) return 1;
     if (encode_map(ctx, &lnmaps[1], p.C, 2, dims, strides, box, ones)) return 1;
     if (encode_map(ctx, &lnmaps[2], p.C2, 2, dims, strides, box, ones)) return 1;
+  }
+  if (f16) {   // instantiated for the two GEMMs of the subsampler only (tc_gemm_supported admits nothing else)
+    if (epilogue == EPI_BIAS_RELU && bn == 144) return launch_one<EPI_BIAS_RELU, 144, 128, true>(ctx, ma, mb, lnmaps, tp, stream);
+    if (epilogue == EPI_BIAS_RELU && bn == 256) return launch_one<EPI_BIAS_RELU, 256, 128, true>(ctx, ma, mb, lnmaps, tp, stream);
+    if (epilogue == EPI_BIAS_LN && bn == 144 && bm == 64) return launch_one<EPI_BIAS_LN, 144, 64, true>(ctx, ma, mb, lnmaps, tp, stream);
+    if (epilogue == EPI_BIAS_LN && bn == 144 && bm == 128) return launch_one<EPI_BIAS_LN, 144, 128, true>(ctx, ma, mb, lnmaps, tp, stream);
+    if (epilogue == EPI_BIAS_LN && bn == 256 && bm == 64) return launch_one<EPI_BIAS_LN, 256, 64, true>(ctx, ma, mb, lnmaps, tp, stream);
+    if (epilogue == EPI_BIAS_LN && bn == 256 && bm == 128) return launch_one<EPI_BIAS_LN, 256, 128, true>(ctx, ma, mb, lnmaps, tp, stream);
+    snprintf(g_errbuf, sizeof(g_errbuf), "gemm_tc: no fp16-operand kernel for epilogue %d, tile %d x %d", epilogue, bm, bn);
+    return 1;
   }
   if (bn == 224) return launch_one<EPI_NONE, 224, 128>(ctx, ma, mb, lnmaps, tp, stream);
   if (bm == 64) {

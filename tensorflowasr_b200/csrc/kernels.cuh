@@ -71,9 +71,11 @@ struct GemmParams {
   // tcgen05 path: store C (plain epilogues) / C2 (LayerNorm epilogues) rounded to nearest tf32 -- set when the tensor is only
   // read as a tensor-core operand again (the datapath would truncate raw fp32 bits)
   int round_out = 0;
-  // tcgen05 path, a_mode 1 only: A (the conv1 map) and W hold IEEE fp16 -- products of 11-bit significands accumulated in fp32, exactly
-  // what kind::tf32 computes on tf32-rounded operands, at twice the MMA rate and half the operand bytes
+  // tcgen05 path (conv2: a_mode 1 + EPI_BIAS_RELU; subsampling linear layer: a_mode 0 + EPI_BIAS_LN): A and W hold IEEE fp16 --
+  // products of 11-bit significands accumulated in fp32, exactly what kind::tf32 computes on tf32-rounded operands, at twice the MMA
+  // rate and half the operand bytes.  lda counts halves then.
   int f16 = 0;
+  int out_f16 = 0;     // plain epilogues: C holds IEEE fp16 [M, ldc] (ldc in halves)
 };
 int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream);
 

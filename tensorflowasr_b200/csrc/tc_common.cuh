@@ -2,6 +2,7 @@
 // tcgen05 (mma, ld, st, commit, fences), UMMA descriptors, fused epilogues, tensor-map encoding.
 #pragma once
 #include "gemm_tc.cuh"
+#include <cuda_fp16.h>
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -32,6 +33,7 @@ struct TcParams {
   int a_mode, T2, F2, D, bt, kc, pad_t, pad_f, tiles_per_b;
   int round_out;   // plain epilogues: store C rounded to nearest tf32 (it is only read as a tensor-core operand again)
   int f16;         // A and B operands hold IEEE fp16 (kind::f16, 64 columns per 128-byte swizzle row, K = 16 per instruction)
+  int out_f16;     // plain epilogues: C holds IEEE fp16 [M, ldc] (it is only read as an fp16 tensor-core operand again)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -200,6 +202,28 @@ __device__ __forceinline__ void warp_tile_store(float* wsm, const float* v, floa
   }
   __syncwarp();
 }
+// the same with an fp16 destination (row segments of 2 * W bytes)
+template <int W>
+__device__ __forceinline__ void warp_tile_store_h(float* wsm, const float* v, __half* gtile, size_t ld, int nrows, int ncols, int lane) {
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) *reinterpret_cast<float4*>(wsm + lane * kWsmLd + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  constexpr int CH = W / 4, RPI = 32 / CH;
+  const int q = lane % CH;
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + lane / CH;
+    if (r < nrows && 4 * q < ncols) {
+      const float4 t = *reinterpret_cast<const float4*>(wsm + r * kWsmLd + 4 * q);
+      const __half2 h01 = __floats2half2_rn(t.x, t.y), h23 = __floats2half2_rn(t.z, t.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const unsigned int*>(&h01);
+      pk.y = *reinterpret_cast<const unsigned int*>(&h23);
+      *reinterpret_cast<uint2*>(gtile + (size_t)r * ld + 4 * q) = pk;
+    }
+  }
+  __syncwarp();
+}
 template <int W>
 __device__ __forceinline__ void warp_tile_load(float* wsm, float* v, const float* gtile, size_t ld, int nrows, int ncols, int lane) {
   constexpr int CH = W / 4, RPI = 32 / CH;
@@ -253,7 +277,8 @@ __device__ __forceinline__ void epilogue_plain_group(const TcParams& p, uint32_t
       else if (EPI == EPI_RESID) v[i] = r[i] + p.alpha * v[i];
       if (p.round_out) v[i] = __uint_as_float(tf32_rn_bits(v[i]));
     }
-    warp_tile_store<W>(wsm, v, p.C + grow0 * p.ldc + gcol, p.ldc, nrows, p.N - gcol, lane);
+    if (p.out_f16) warp_tile_store_h<W>(wsm, v, reinterpret_cast<__half*>(p.C) + grow0 * p.ldc + gcol, p.ldc, nrows, p.N - gcol, lane);   // warp-uniform
+    else warp_tile_store<W>(wsm, v, p.C + grow0 * p.ldc + gcol, p.ldc, nrows, p.N - gcol, lane);
   }
 }
 

@@ -691,6 +691,10 @@ def device_tensors(enc_geo: ModelGeometry, enc_raw: Dict[str, np.ndarray], ctc_g
         w16 = out["sub.conv2.w"].astype(np.float16)
         if np.isfinite(w16).all() and (D * 9 * D) % 2 == 0:
             out["sub.conv2.w16"] = np.ascontiguousarray(w16).view(np.float32).reshape(-1)
+            # ... and the subsampling linear layer's, which then reads conv2's output as fp16 as well
+            l16 = out["sub.lin.w"].astype(np.float16)
+            if np.isfinite(l16).all() and l16.size % 2 == 0:
+                out["sub.lin.w16"] = np.ascontiguousarray(l16).view(np.float32).reshape(-1)
     return out
 
 
