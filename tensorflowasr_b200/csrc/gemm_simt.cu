@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(256) conv1_kernel(const Conv1Params p, int gro
   }
 }
 
+// (An eight-channels-per-thread variant of the fp16-output path -- nine shared loads feeding 36 packed FMAs instead of 18 -- was
+// measured SLOWER: 98.7 us against 76.7 us; the kernel needs the parallelism of four channels per thread more than the saved loads.)
 // Second generation of conv1: same mapping, but the mel patch is staged as (m, m) pairs and the four channels of a thread are
 // two packed fp32x2 accumulators, so a tap costs one 8-byte shared load + two fma.rn.f32x2 instead of one load + four FFMA
 // (the kernel is issue-bound: 68 M warp instructions for 369 MB of output).  Bit-identical results: f32x2 is two independent
@@ -260,75 +262,6 @@ __global__ void __launch_bounds__(256) conv1_f32x2_kernel(const Conv1Params p, i
   }
 }
 
-// fp16-output variant with EIGHT channels per thread: the kernel is issue-bound, and the nine 8-byte shared loads of a window now feed
-// 36 packed FMAs instead of 18 (one 16-byte store per output position and thread).
-__global__ void __launch_bounds__(256) conv1_h8_kernel(const Conv1Params p, int groups, int flanes) {
-  extern __shared__ __align__(8) float2 mel2_s[];  // [2*ROWS+1][F + 2] of (m, m), one zero column of padding on each side
-  pdl_trigger();
-  pdl_wait();
-  const int b = blockIdx.y;
-  const int t1_0 = blockIdx.x * kConv1Rows;
-  const int FW = p.F + 2;
-  const int nrows = 2 * kConv1Rows + 1;
-  for (int i = threadIdx.x; i < nrows * FW; i += blockDim.x) {
-    const int r = i / FW, xx = i - r * FW;
-    const int y = 2 * t1_0 + r - p.pad_t;
-    const int x = xx - 1;
-    float v = 0.f;
-    if (y >= 0 && y < p.T && x >= 0 && x < p.F) v = p.mel[((size_t)b * p.T + y) * p.F + x];
-    mel2_s[i] = make_float2(v, v);
-  }
-  const int g = threadIdx.x % groups, fl = threadIdx.x / groups;
-  unsigned long long w[9][4], bias[4];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-#pragma unroll
-    for (int hq = 0; hq < 2; ++hq) {
-      const float4 ww = *reinterpret_cast<const float4*>(p.w + k * p.D + 8 * g + 4 * hq);
-      float2 lo = make_float2(ww.x, ww.y), hi = make_float2(ww.z, ww.w);
-      w[k][2 * hq] = *reinterpret_cast<unsigned long long*>(&lo);
-      w[k][2 * hq + 1] = *reinterpret_cast<unsigned long long*>(&hi);
-    }
-  }
-#pragma unroll
-  for (int hq = 0; hq < 2; ++hq) {
-    const float4 bb = *reinterpret_cast<const float4*>(p.bias + 8 * g + 4 * hq);
-    float2 lo = make_float2(bb.x, bb.y), hi = make_float2(bb.z, bb.w);
-    bias[2 * hq] = *reinterpret_cast<unsigned long long*>(&lo);
-    bias[2 * hq + 1] = *reinterpret_cast<unsigned long long*>(&hi);
-  }
-  __syncthreads();
-  if (fl >= flanes) return;
-  __half* out_h = reinterpret_cast<__half*>(p.out);
-  for (int r = 0; r < kConv1Rows; ++r) {
-    const int t1 = t1_0 + r;
-    if (t1 >= p.T1) break;
-    __half* hrow = out_h + (((size_t)b * p.T1 + t1) * p.F1) * p.D + 8 * g;
-    for (int f1 = fl; f1 < p.F1; f1 += flanes) {
-      unsigned long long a[4] = {bias[0], bias[1], bias[2], bias[3]};
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const unsigned long long* mrow = reinterpret_cast<const unsigned long long*>(mel2_s + (2 * r + kh) * FW + (2 * f1 - p.pad_f + 1));
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const unsigned long long m = mrow[kw];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = ffma2_u64(m, w[kh * 3 + kw][j], a[j]);
-        }
-      }
-      uint4 pk;
-      unsigned int* pw = reinterpret_cast<unsigned int*>(&pk);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 v = *reinterpret_cast<float2*>(&a[j]);
-        const __half2 h = __floats2half2_rn(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
-        pw[j] = *reinterpret_cast<const unsigned int*>(&h);
-      }
-      *reinterpret_cast<uint4*>(hrow + (size_t)f1 * p.D) = pk;
-    }
-  }
-}
-
 }  // namespace
 
 int launch_gemm_simt(const GemmParams& p, int epilogue, cudaStream_t stream) {
@@ -363,17 +296,6 @@ int launch_conv1(const Conv1Params& p, cudaStream_t stream) {
   if (legacy && p.out_f16) {
     snprintf(g_errbuf, sizeof(g_errbuf), "conv1: the legacy kernel (B200ASR_CONV1_LEGACY=1) has no fp16 output");
     return 1;
-  }
-  static int h4 = -1;
-  if (h4 < 0) {
-    const char* e = getenv("B200ASR_CONV1_H4");       // 1: fp16 output through the four-channels-per-thread kernel (A/B switch)
-    h4 = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (!legacy && p.out_f16 && !h4 && p.D % 8 == 0) {
-    const int g8 = p.D / 8, fl8 = 256 / g8;
-    B200_CUDA_OK(launch_k(conv1_h8_kernel, grid, dim3(g8 * fl8), 2 * smem, stream, p, g8, fl8));
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
   }
   if (!legacy) {
     B200_CUDA_OK(launch_k(conv1_f32x2_kernel, grid, dim3(threads), 2 * smem, stream, p, groups, flanes));
