@@ -155,3 +155,42 @@ def test_chunk_weight_packing_layout():
     blob = CM.pack_chunk_blob(raw, geo)
     assert blob[:8] == b"B2ASRW01"
     assert ctypes.sizeof(CM.ChunkConfig) == 4 * 22 + 4 * 8
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under tensorflowasr_b200/ (the product) may import or execute oracle/, and bench.py's
+    own arm only does so in its cpu_baseline / reference legs (a product path through the oracle would void every parity claim)."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "tensorflowasr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                tree = ast.parse(open(path, encoding="utf-8").read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        names = [node.module or ""]
+                    assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+            if f.endswith((".cu", ".cuh", ".h", ".py")):
+                text = open(path, encoding="utf-8").read()
+                assert "oracle/_ref" not in text and "oracle/" not in text.replace("# oracle", ""), path
+    # bench.py: oracle imports only inside the CPU legs
+    tree = ast.parse(open(os.path.join(root, "bench.py"), encoding="utf-8").read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, (ast.Import, ast.ImportFrom)) and any("oracle" in (a.name if isinstance(n, ast.Import) else (n.module or "")) for a in n.names)
+                   for n in ast.walk(fn))
+        if uses:
+            assert fn.name in ("cpu_reference_step", "reference_arm", "cpu_baseline_sample", "_ort_threads_best"), fn.name
+
+
+def test_every_entry_point_of_the_header_is_bound_or_documented():
+    """include/b200asr.h cites, for each entry point family, the reference interface it replaces (file:line)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "b200asr.h"), encoding="utf-8").read()
+    for cite in ("asr.py", "asr_session.cpp", "ctc_beam_search_decoder", "chunk_conformer_blocks.py", "vad/src/vad.py", "punc_recover.py",
+                 "am_tester.py"):
+        assert cite in text, cite

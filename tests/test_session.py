@@ -154,3 +154,36 @@ def test_punctuation_oracle_is_pinned_to_the_reference(gold):
     assert dev["l0.qkv.w"].shape == (192, 64) and dev["c1.w"].shape == (64, 192) and dev["up.w"].shape == (768, 64)
     np.testing.assert_allclose(dev["l2.qkv.w"][:64], raw["l2.q.w"].T / np.sqrt(8.0), rtol=1e-6)
     np.testing.assert_array_equal(dev["c0.w"][:, 64:128], raw["c0.w"][:, :, 1])
+
+
+def test_stream_session_tolerates_ragged_packets(gold):
+    """Packets that are not whole 160-sample frames (100 samples each): the reference's reshape would raise; here the VAD window drops
+    the ragged head and the session keeps producing well-formed events."""
+    script = gold["script2"].astype(np.int32)
+    sess = S.StreamASRSession(ScriptASR(), ScriptVAD(script), None)
+    pcm = script_pcm(len(script) * 1600)
+    events = []
+    for p in range(0, len(pcm), 100):
+        r = sess.send(pcm[p:p + 100].tobytes())
+        if r is not None:
+            events.append(r)
+    r = sess.final_send()
+    if r is not None:
+        events.append(r)
+    kinds = [e["event_type"] for e in events]
+    assert kinds.count("sentence begin") >= 1 and kinds.count("sentence end") >= 1
+    for e in events:
+        if e["event_type"] == "sentence end":
+            assert e["sentence_end_time"] >= e["sentence_begin_time"] and e["best_text"].startswith("decode(")
+    assert sess.send(b"") is None          # an empty packet is a no-op
+
+
+def test_offline_vad_without_speech_returns_nothing():
+    class Quiet:
+        def inference(self, wav):
+            return -np.ones((1, wav.shape[1], 1), np.float32)
+    ov = S.OfflineVAD(sr=16000)
+    ov.compile(Quiet())
+    assert ov.vad(np.zeros(32000, np.float32)) == []
+    sess = S.OfflineASRSession(ScriptASR(), Quiet(), None)
+    assert sess.send(np.zeros(32000 + 77, np.float32)) == []
