@@ -324,3 +324,26 @@ def read_exported(path: str) -> Optional[Dict[str, np.ndarray]]:
     g = R.load_graph(path)
     raw = {k[len(PREFIX):]: np.asarray(v) for k, v in g.initializers.items() if k.startswith(PREFIX)}
     return raw or None
+
+
+def main(argv=None) -> int:
+    """python -m tensorflowasr_b200.onnx_export IN_DIR OUT_DIR: read encoder.onnx / ctc_model.onnx (/ translator.onnx) of a deployment
+    directory (the reference's tf2onnx files or files written here) and write them again through this exporter."""
+    import argparse
+    import os
+    from . import weights as W
+    ap = argparse.ArgumentParser(prog="python -m tensorflowasr_b200.onnx_export", description=main.__doc__)
+    ap.add_argument("in_dir")
+    ap.add_argument("out_dir")
+    a = ap.parse_args(argv)
+    enc = W.import_encoder(os.path.join(a.in_dir, "encoder.onnx"))
+    ctc = W.import_ctc_model(os.path.join(a.in_dir, "ctc_model.onnx"))
+    tr_path = os.path.join(a.in_dir, "translator.onnx")
+    tr = W.import_translator(tr_path) if os.path.isfile(tr_path) else None
+    export_model_dir(a.out_dir, enc, ctc, tr)
+    print("wrote", ", ".join(sorted(f for f in os.listdir(a.out_dir) if f.endswith(".onnx"))), "to", a.out_dir)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

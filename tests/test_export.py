@@ -114,3 +114,16 @@ def test_random_model_exports_and_runs(ort, tmp_path):
     lg = ort.OrtModel(str(tmp_path / "ctc_model.onnx"), 4).run({"inputs": e})
     want = conformer_ref.ctc_forward(e, rc, gc.num_blocks)
     assert np.abs(lg - want).max() < 2e-3
+
+
+def test_command_line_round_trip(ort, tmp_path):
+    """python -m tensorflowasr_b200.onnx_export IN OUT on the shipped directory, then once more on its own output: same bytes."""
+    import subprocess
+    import sys
+    d = ort.model_dir("offline")
+    a, b = tmp_path / "a", tmp_path / "b"
+    for src, dst in ((d, a), (str(a), b)):
+        r = subprocess.run([sys.executable, "-m", "tensorflowasr_b200.onnx_export", src, str(dst)], cwd=ROOT, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    for f in ("encoder.onnx", "ctc_model.onnx"):
+        assert (a / f).read_bytes() == (b / f).read_bytes()
