@@ -318,14 +318,6 @@ def export_model_dir(out_dir: str, enc=None, ctc=None, translator=None) -> None:
         export_translator(translator[0], translator[1], os.path.join(out_dir, "translator.onnx"))
 
 
-def read_exported(path: str) -> Optional[Dict[str, np.ndarray]]:
-    """The `raw` dictionary of a file this module wrote (initializers under PREFIX), or None for any other ONNX file."""
-    from . import onnx_reader as R
-    g = R.load_graph(path)
-    raw = {k[len(PREFIX):]: np.asarray(v) for k, v in g.initializers.items() if k.startswith(PREFIX)}
-    return raw or None
-
-
 def main(argv=None) -> int:
     """python -m tensorflowasr_b200.onnx_export IN_DIR OUT_DIR: read encoder.onnx / ctc_model.onnx (/ translator.onnx) of a deployment
     directory (the reference's tf2onnx files or files written here) and write them again through this exporter."""
