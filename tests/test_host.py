@@ -194,3 +194,20 @@ def test_every_entry_point_of_the_header_is_bound_or_documented():
     for cite in ("asr.py", "asr_session.cpp", "ctc_beam_search_decoder", "chunk_conformer_blocks.py", "vad/src/vad.py", "punc_recover.py",
                  "am_tester.py"):
         assert cite in text, cite
+
+
+def test_fp16_subsampler_operands_are_packed_exactly():
+    """tf32 mode: conv2 / subsampling-linear weights travel a second time as IEEE fp16, two per float32 word of the blob; a tf32-rounded
+    weight in fp16's normal range converts without any further rounding (same 11-bit significand)."""
+    from tensorflowasr_b200 import weights as W
+    ge, re_, gc, rc = W.random_model(2, num_blocks=1)
+    dev = W.device_tensors(ge, re_, gc, rc, round_tf32=True)
+    D = ge.dmodel
+    for key, shape in (("sub.conv2.w", (D, 9 * D)), ("sub.lin.w", (D, re_["sub.lin.w"].shape[0]))):
+        w32 = dev[key]
+        w16 = dev[key + "16"].view(np.float16).reshape(shape)
+        assert dev[key + "16"].dtype == np.float32 and dev[key + "16"].size * 2 == w32.size
+        normal = np.abs(w32) >= 6.2e-5
+        np.testing.assert_array_equal(w16.astype(np.float32)[normal], w32[normal])          # exact where fp16 is normal
+        assert np.abs(w16.astype(np.float32) - w32)[~normal].max(initial=0.0) <= 3.0e-8      # subnormal tail: absolute 2^-25
+    assert "sub.conv2.w16" not in W.device_tensors(ge, re_, gc, rc, round_tf32=False)        # the exact-fp32 mode keeps fp32 only
